@@ -1,0 +1,380 @@
+// eikws-b200: C ABI (include/eikws_b200.h).  Thin host layer: model container -> plan -> kernel launches.
+// No CPU compute path exists here; every classify/features call launches the CUDA kernel or fails.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "eikws_b200.h"
+#include "kernels.h"
+#include "model_graph.h"
+#include "plan.h"
+
+namespace eikws {
+bool capture_compiled_model(const eikws_compiled_model_t *cm, ModelGraph &g, std::string &err);
+}
+
+using namespace eikws;
+
+struct eikws_handle {
+    int device = 0;
+    ModelGraph graph;
+    HostPlan host;
+    DevicePlan dev;
+    int sm_count = 148;
+    int ctas_per_sm = 3;
+    uint64_t launches = 0;
+    std::mutex mu;  // serialises the host-buffer and single-clip paths (they share staging buffers)
+    // staging for the host-buffer entry points
+    void *d_in = nullptr;
+    size_t d_in_bytes = 0;
+    float *d_probs = nullptr;
+    size_t d_probs_bytes = 0;
+    float *d_feat = nullptr;
+    size_t d_feat_bytes = 0;
+    int8_t *d_qfeat = nullptr;
+    size_t d_qfeat_bytes = 0;
+    float *h_pinned = nullptr;  // one clip of floats for eikws_run_classifier_signal
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+thread_local std::string t_err;
+int fail(int code, const std::string &msg) {
+    t_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    t_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return EIKWS_ERR_CUDA;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int ensure(void **p, size_t *have, size_t need) {
+    if (*have >= need) return EIKWS_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(staging)");
+    *have = need;
+    return EIKWS_OK;
+}
+
+int grid_for(const eikws_handle *h, size_t n_clips) {
+    size_t g = static_cast<size_t>(h->sm_count) * h->ctas_per_sm;  // persistent: one wave of resident CTAs
+    if (n_clips < g) g = n_clips;
+    return static_cast<int>(g ? g : 1);
+}
+
+int launch(eikws_handle *h, const void *clips, bool f32, const float *features_in, size_t n, bool run_nn, float *probs,
+           float *feat, int8_t *qfeat, cudaStream_t st) {
+    if (n == 0) return EIKWS_OK;
+    if (clips && (reinterpret_cast<uintptr_t>(clips) & 15)) return fail(EIKWS_ERR_BAD_ARG, "clip buffer must be 16-byte aligned (TMA bulk copy)");
+    LaunchArgs a;
+    a.plan = h->dev.d_plan;
+    a.clips = clips;
+    a.input_is_f32 = f32;
+    a.features_in = features_in;
+    a.n_clips = n;
+    a.run_nn = run_nn;
+    a.probs = probs;
+    a.features_out = feat;
+    a.qfeatures_out = qfeat;
+    a.grid = grid_for(h, n);
+    a.nn_smem_bytes = h->dev.nn_smem_bytes;
+    a.stream = st;
+    cudaError_t e = launch_run_classifier(a);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    h->launches++;
+    return EIKWS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char *eikws_last_error(void) { return t_err.c_str(); }
+
+int eikws_model_from_compiled(const eikws_compiled_model_t *cm, void **blob, size_t *bytes) {
+    if (!blob || !bytes) return fail(EIKWS_ERR_BAD_ARG, "null output argument");
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    ModelGraph g;
+    std::string err;
+    if (!capture_compiled_model(cm, g, err)) return fail(EIKWS_ERR_TFLITE, err);
+    std::vector<uint8_t> out;
+    serialize_model(g, out);
+    void *p = std::malloc(out.size());
+    if (!p) return fail(EIKWS_ERR_ALLOC_FAILED, "malloc failed");
+    std::memcpy(p, out.data(), out.size());
+    *blob = p;
+    *bytes = out.size();
+    return EIKWS_OK;
+}
+
+void eikws_free(void *p) { std::free(p); }
+
+int eikws_create(const void *model_blob, size_t bytes, int device, eikws_handle **out) {
+    if (!out) return fail(EIKWS_ERR_BAD_ARG, "null output argument");
+    *out = nullptr;
+    eikws_handle *h = new (std::nothrow) eikws_handle();
+    if (!h) return fail(EIKWS_ERR_ALLOC_FAILED, "out of memory");
+    std::string err;
+    if (!parse_model(model_blob, bytes, h->graph, err)) {
+        delete h;
+        return fail(EIKWS_ERR_BAD_ARG, err);
+    }
+    int rc = build_host_plan(h->graph, h->host, err);
+    if (rc != EIKWS_OK) {
+        delete h;
+        return fail(rc, err);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        delete h;
+        return fail(EIKWS_ERR_CUDA, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= ndev) {
+        delete h;
+        return fail(EIKWS_ERR_BAD_ARG, "device index out of range");
+    }
+    h->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete h;
+        return fail(EIKWS_ERR_CUDA, "cudaSetDevice failed");
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaGetDeviceProperties");
+    }
+    if (prop.major < 10) {
+        delete h;
+        return fail(EIKWS_ERR_CUDA, "this library contains sm_100a code only; device compute capability is " + std::to_string(prop.major) + "." +
+                                        std::to_string(prop.minor));
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = upload_plan(h->host, h->dev)) != cudaSuccess) {
+        free_plan(h->dev);
+        delete h;
+        return cuda_fail(e, "plan upload");
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        free_plan(h->dev);
+        delete h;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = h;
+    return EIKWS_OK;
+}
+
+void eikws_destroy(eikws_handle *h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_probs) cudaFree(h->d_probs);
+    if (h->d_feat) cudaFree(h->d_feat);
+    if (h->d_qfeat) cudaFree(h->d_qfeat);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    free_plan(h->dev);
+    delete h;
+}
+
+int eikws_label_count(const eikws_handle *h) { return h ? static_cast<int>(h->graph.labels.size()) : 0; }
+int eikws_feature_count(const eikws_handle *h) { return h ? static_cast<int>(h->graph.nn_input_frame_size) : 0; }
+int eikws_raw_sample_count(const eikws_handle *h) { return h ? static_cast<int>(h->graph.raw_sample_count) : 0; }
+int eikws_device(const eikws_handle *h) { return h ? h->device : -1; }
+const char *eikws_label(const eikws_handle *h, int i) {
+    if (!h || i < 0 || i >= static_cast<int>(h->graph.labels.size())) return nullptr;
+    return h->graph.labels[i].c_str();
+}
+uint64_t eikws_launch_count(const eikws_handle *h) { return h ? h->launches : 0; }
+
+int eikws_set_ctas_per_sm(eikws_handle *h, int n) {  // tuning knob (not in the public header)
+    if (!h || n < 1 || n > 8) return EIKWS_ERR_BAD_ARG;
+    h->ctas_per_sm = n;
+    return EIKWS_OK;
+}
+
+// ---- device-buffer entry points -------------------------------------------------------------------------
+int eikws_classify_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n, float *d_probs, void *stream) {
+    if (!h || !d_pcm || !d_probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, d_pcm, false, nullptr, n, true, d_probs, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+int eikws_classify_f32_device(eikws_handle *h, const float *d_samples, size_t n, float *d_probs, void *stream) {
+    if (!h || !d_samples || !d_probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, d_samples, true, nullptr, n, true, d_probs, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+int eikws_features_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n, float *d_features, int8_t *d_q, void *stream) {
+    if (!h || !d_pcm || (!d_features && !d_q)) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, d_pcm, false, nullptr, n, false, nullptr, d_features, d_q, static_cast<cudaStream_t>(stream));
+}
+int eikws_features_f32_device(eikws_handle *h, const float *d_samples, size_t n, float *d_features, int8_t *d_q, void *stream) {
+    if (!h || !d_samples || (!d_features && !d_q)) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, d_samples, true, nullptr, n, false, nullptr, d_features, d_q, static_cast<cudaStream_t>(stream));
+}
+int eikws_infer_device(eikws_handle *h, const float *d_features, size_t n, float *d_probs, void *stream) {
+    if (!h || !d_features || !d_probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, nullptr, false, d_features, n, true, d_probs, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+// debug/parity tap: classify and also return float + int8 features
+int eikws_classify_taps_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n, float *d_probs, float *d_features, int8_t *d_q,
+                                   void *stream) {
+    if (!h || !d_pcm || !d_probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch(h, d_pcm, false, nullptr, n, true, d_probs, d_features, d_q, static_cast<cudaStream_t>(stream));
+}
+
+int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n, uint64_t first_clip, uint64_t seed, void *stream) {
+    if (!h || !d_pcm) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    cudaError_t e = launch_synth(d_pcm, n, first_clip, seed, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "synth launch");
+    return EIKWS_OK;
+}
+
+// ---- host-buffer entry points (synchronous) ---------------------------------------------------------------
+static int host_run(eikws_handle *h, const void *in, size_t in_bytes_per_clip, bool f32, const float *features_in, size_t n, bool run_nn,
+                    float *probs, float *features, int8_t *qfeatures) {
+    if (n == 0) return EIKWS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t L = h->graph.labels.size(), F = h->graph.nn_input_frame_size;
+    int rc;
+    cudaError_t e;
+    const void *d_src = nullptr;
+    if (features_in) {
+        if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
+        if ((e = cudaMemcpyAsync(h->d_feat, features_in, n * F * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
+            return cuda_fail(e, "H2D features");
+    } else {
+        if ((rc = ensure(&h->d_in, &h->d_in_bytes, n * in_bytes_per_clip))) return rc;
+        if ((e = cudaMemcpyAsync(h->d_in, in, n * in_bytes_per_clip, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
+            return cuda_fail(e, "H2D clips");
+        d_src = h->d_in;
+        if (features && (rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
+    }
+    if (probs && (rc = ensure(reinterpret_cast<void **>(&h->d_probs), &h->d_probs_bytes, n * L * 4))) return rc;
+    if (qfeatures && (rc = ensure(reinterpret_cast<void **>(&h->d_qfeat), &h->d_qfeat_bytes, n * F))) return rc;
+    rc = launch(h, d_src, f32, features_in ? h->d_feat : nullptr, n, run_nn, probs ? h->d_probs : nullptr,
+                (features && !features_in) ? h->d_feat : nullptr, qfeatures ? h->d_qfeat : nullptr, h->stream);
+    if (rc) return rc;
+    if (probs && (e = cudaMemcpyAsync(probs, h->d_probs, n * L * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        return cuda_fail(e, "D2H probs");
+    if (features && !features_in && (e = cudaMemcpyAsync(features, h->d_feat, n * F * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        return cuda_fail(e, "D2H features");
+    if (qfeatures && (e = cudaMemcpyAsync(qfeatures, h->d_qfeat, n * F, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        return cuda_fail(e, "D2H qfeatures");
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
+    return EIKWS_OK;
+}
+
+int eikws_classify_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *probs) {
+    if (!h || !pcm || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, pcm, static_cast<size_t>(kSamples) * 2, false, nullptr, n, true, probs, nullptr, nullptr);
+}
+int eikws_classify_f32_host(eikws_handle *h, const float *samples, size_t n, float *probs) {
+    if (!h || !samples || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, samples, static_cast<size_t>(kSamples) * 4, true, nullptr, n, true, probs, nullptr, nullptr);
+}
+int eikws_features_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *features, int8_t *qfeatures) {
+    if (!h || !pcm || (!features && !qfeatures)) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, pcm, static_cast<size_t>(kSamples) * 2, false, nullptr, n, false, nullptr, features, qfeatures);
+}
+int eikws_features_f32_host(eikws_handle *h, const float *samples, size_t n, float *features, int8_t *qfeatures) {
+    if (!h || !samples || (!features && !qfeatures)) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, samples, static_cast<size_t>(kSamples) * 4, true, nullptr, n, false, nullptr, features, qfeatures);
+}
+int eikws_infer_host(eikws_handle *h, const float *features, size_t n, float *probs) {
+    if (!h || !features || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, nullptr, 0, false, features, n, true, probs, nullptr, nullptr);
+}
+int eikws_classify_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *probs, float *features, int8_t *qfeatures) {
+    if (!h || !pcm || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return host_run(h, pcm, static_cast<size_t>(kSamples) * 2, false, nullptr, n, true, probs, features, qfeatures);
+}
+
+// ---- single clip through the reference's pull callback -----------------------------------------------------
+// run_classifier (ei_run_classifier.h:650-714).  The reference pulls the signal in ~98 pieces
+// ((off,320) frames and (off-1,1) history samples); any call pattern is legal, so the whole clip is pulled once.
+int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *values, int *t_dsp_ms,
+                                int *t_cls_ms) {
+    if (!h || !get_data || !values) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    // extract_mfcc_features fails with EIDSP_MATRIX_SIZE_MISMATCH -> EI_IMPULSE_DSP_ERROR when the signal would
+    // produce more features than the block owns (ei_run_dsp.h:279-283); the kernel is specialised to exactly
+    // EI_CLASSIFIER_RAW_SAMPLE_COUNT samples.
+    if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard guard(h->device);
+        if (!h->h_pinned) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        }
+    }
+    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
+    int rc = eikws_classify_f32_host(h, h->h_pinned, 1, values);
+    auto t1 = std::chrono::steady_clock::now();
+    // the fused kernel does DSP and classification in one launch; the whole latency is reported as dsp
+    if (t_dsp_ms) *t_dsp_ms = static_cast<int>(std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
+    if (t_cls_ms) *t_cls_ms = 0;
+    return rc;
+}
+
+// ---- parity taps of host-side derived data (tests only; no GPU needed) ------------------------------------------
+int eikws_debug_host_plan(const void *model_blob, size_t bytes, float *filterbank_129x32, int32_t *conv_mult, int32_t *conv_shift,
+                          int max_channels, int *n_channels) {
+    ModelGraph g;
+    HostPlan hp;
+    std::string err;
+    if (!parse_model(model_blob, bytes, g, err)) return fail(EIKWS_ERR_BAD_ARG, err);
+    int rc = build_host_plan(g, hp, err);
+    if (rc) return fail(rc, err);
+    if (filterbank_129x32) std::memcpy(filterbank_129x32, hp.filterbank.data(), hp.filterbank.size() * sizeof(float));
+    int n = 0;
+    for (int o = 0; o < hp.dev.nn.n_ops; o++) {
+        const NnOpDev &op = hp.dev.nn.ops[o];
+        if (op.kind != kNnConv1d) continue;
+        // pointers are still null on the host image; find this op's tables through the fixups
+        size_t moff = 0, soff = 0;
+        for (const auto &f : hp.fixups) {
+            const uint8_t *base = reinterpret_cast<const uint8_t *>(&hp.dev);
+            if (base + f.first == reinterpret_cast<const uint8_t *>(&op.mult)) moff = f.second;
+            if (base + f.first == reinterpret_cast<const uint8_t *>(&op.shift)) soff = f.second;
+        }
+        for (int c = 0; c < op.out_c && n < max_channels; c++, n++) {
+            if (conv_mult) std::memcpy(&conv_mult[n], hp.blob.data() + moff + 4 * c, 4);
+            if (conv_shift) std::memcpy(&conv_shift[n], hp.blob.data() + soff + 4 * c, 4);
+        }
+    }
+    if (n_channels) *n_channels = n;
+    return EIKWS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// eikws-b200: host-callable launchers of kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "dev_plan.h"
+
+namespace eikws {
+
+struct LaunchArgs {
+    const DevPlan *plan = nullptr;       // device pointer
+    const void *clips = nullptr;         // device: [n_clips][16000] int16 or float
+    bool input_is_f32 = false;
+    const float *features_in = nullptr;  // device: run_inference only (clips ignored)
+    size_t n_clips = 0;
+    bool run_nn = true;
+    float *probs = nullptr;              // device: [n_clips][labels]
+    float *features_out = nullptr;       // device, optional: [n_clips][637]
+    int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
+    int grid = 0;
+    int nn_smem_bytes = 0;               // activation arena + conv row scratch
+    cudaStream_t stream = nullptr;
+};
+
+cudaError_t launch_run_classifier(const LaunchArgs &a);
+cudaError_t launch_synth(int16_t *pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, cudaStream_t st);
+int kernel_threads();
+// bytes of shared memory available to the classifier arena inside the fused kernel's overlay
+int nn_smem_capacity(bool input_is_f32);
+
+}  // namespace eikws

@@ -1,0 +1,127 @@
+/* eikws_b200.h -- C ABI of libeikws_b200.so
+ *
+ * B200-native (sm_100a CUDA) implementation of the hot path of ShawnHymel/ei-keyword-spotting:
+ *     run_classifier(signal_t*, ei_impulse_result_t*, bool)
+ *         edge-impulse-sdk/classifier/ei_run_classifier.h:650-714
+ *   = extract_mfcc_features   edge-impulse-sdk/classifier/ei_run_dsp.h:256-308
+ *   + run_inference           edge-impulse-sdk/classifier/ei_run_classifier.h:293-641
+ * Plain pointers and sizes only; no C++/torch types.  Error returns use the reference's
+ * EI_IMPULSE_ERROR values (edge-impulse-sdk/porting/ei_classifier_porting.h:34-43) plus the
+ * EIKWS_* extensions below.  There is no CPU compute fallback: every classify/features call
+ * runs CUDA kernels or fails.
+ *
+ * The reference processes one clip per call through a pull callback; one callback per clip
+ * cannot feed a GPU, so the batch entry points take contiguous clips
+ * ([n_clips][raw_sample_count], int16 PCM or float) -- same arithmetic per clip.
+ */
+#ifndef EIKWS_B200_H
+#define EIKWS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* EI_IMPULSE_ERROR values (ei_classifier_porting.h:34-43) */
+#define EIKWS_OK 0
+#define EIKWS_ERR_SHAPES_DONT_MATCH (-1)
+#define EIKWS_ERR_CANCELED (-2)
+#define EIKWS_ERR_TFLITE (-3)
+#define EIKWS_ERR_DSP (-5)
+#define EIKWS_ERR_TFLITE_ARENA_ALLOC_FAILED (-6)
+#define EIKWS_ERR_ALLOC_FAILED (-8)
+/* extensions */
+#define EIKWS_ERR_UNSUPPORTED (-100) /* model/DSP configuration outside what the kernels implement */
+#define EIKWS_ERR_CUDA (-101)        /* CUDA runtime failure (no device, launch error, ...)          */
+#define EIKWS_ERR_BAD_ARG (-102)
+
+typedef struct eikws_handle eikws_handle;
+
+/* What a generated Edge Impulse export provides; filled by the drop-in header
+ * include/edge-impulse-sdk/classifier/ei_run_classifier.h from the UNMODIFIED
+ * model-parameters/model_metadata.h + tflite-model/trained_model_compiled.{h,cpp}. */
+typedef struct {
+    int (*init)(void *(*alloc_fnc)(size_t, size_t)); /* trained_model_init   (trained_model_compiled.cpp:380) */
+    void *(*input)(int index);                       /* trained_model_input  (:446) -> TfLiteTensor*          */
+    void *(*output)(int index);                      /* trained_model_output (:453) -> TfLiteTensor*          */
+    int (*reset)(void (*free_fnc)(void *));          /* trained_model_reset  (:467)                           */
+    uint32_t raw_sample_count;                       /* EI_CLASSIFIER_RAW_SAMPLE_COUNT                        */
+    uint32_t nn_input_frame_size;                    /* EI_CLASSIFIER_NN_INPUT_FRAME_SIZE                     */
+    uint32_t label_count;                            /* EI_CLASSIFIER_LABEL_COUNT                             */
+    int32_t frequency;                               /* EI_CLASSIFIER_FREQUENCY                               */
+    const char *const *labels;                       /* ei_classifier_inferencing_categories                  */
+    /* ei_dsp_config_mfcc_t (model_metadata.h:92-104) */
+    int32_t mfcc_num_cepstral;
+    float mfcc_frame_length;
+    float mfcc_frame_stride;
+    int32_t mfcc_num_filters;
+    int32_t mfcc_fft_length;
+    int32_t mfcc_win_size;
+    int32_t mfcc_low_frequency;
+    int32_t mfcc_high_frequency;
+    float mfcc_pre_cof;
+    int32_t mfcc_pre_shift;
+} eikws_compiled_model_t;
+
+/* ---- model ingestion (host only, no GPU needed) ------------------------------------------- */
+/* Runs the generated model's init against this library's Register_* operators
+ * (replaces TFL/micro/kernels/{conv,add,pooling,fully_connected,softmax,reshape}.cc registrations,
+ * micro_ops.h:33-75) and serialises the recorded graph ("EIKWSMDL" container). *blob is malloc'ed;
+ * release with eikws_free(). */
+int eikws_model_from_compiled(const eikws_compiled_model_t *cm, void **blob, size_t *bytes);
+void eikws_free(void *p);
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+/* Lowers the model to a device plan on CUDA device `device`.  Fails with EIKWS_ERR_CUDA if no
+ * usable GPU, EIKWS_ERR_UNSUPPORTED if the graph/DSP config is outside the implemented family. */
+int eikws_create(const void *model_blob, size_t bytes, int device, eikws_handle **out);
+void eikws_destroy(eikws_handle *h);
+
+int eikws_label_count(const eikws_handle *h);
+int eikws_feature_count(const eikws_handle *h);    /* EI_CLASSIFIER_NN_INPUT_FRAME_SIZE */
+int eikws_raw_sample_count(const eikws_handle *h); /* EI_CLASSIFIER_RAW_SAMPLE_COUNT    */
+int eikws_device(const eikws_handle *h);
+const char *eikws_label(const eikws_handle *h, int i);
+
+/* ---- batch hot path, DEVICE buffers (on the handle's device) ------------------------------- */
+/* run_classifier over n_clips clips of int16 PCM (the demos' signal: int16 -> x/32768,
+ * numpy.hpp:1289-1298).  d_probs: [n_clips][label_count] float = result.classification[i].value.
+ * stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous. */
+int eikws_classify_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n_clips, float *d_probs, void *stream);
+/* same, float samples as a signal_t callback would deliver them */
+int eikws_classify_f32_device(eikws_handle *h, const float *d_samples, size_t n_clips, float *d_probs, void *stream);
+/* extract_mfcc_features only: d_features [n_clips][feature_count] float (may be NULL),
+ * d_qfeatures [n_clips][feature_count] int8 = the quantised NN input (ei_run_classifier.h:436-444; may be NULL) */
+int eikws_features_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n_clips, float *d_features,
+                              int8_t *d_qfeatures, void *stream);
+int eikws_features_f32_device(eikws_handle *h, const float *d_samples, size_t n_clips, float *d_features,
+                              int8_t *d_qfeatures, void *stream);
+/* run_inference only (ei_run_classifier.h:293): float features in, probabilities out */
+int eikws_infer_device(eikws_handle *h, const float *d_features, size_t n_clips, float *d_probs, void *stream);
+
+/* ---- batch hot path, HOST buffers (H2D + kernels + D2H inside the call, synchronous) ------- */
+int eikws_classify_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *probs);
+int eikws_classify_f32_host(eikws_handle *h, const float *samples, size_t n_clips, float *probs);
+int eikws_features_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *features, int8_t *qfeatures);
+int eikws_infer_host(eikws_handle *h, const float *features, size_t n_clips, float *probs);
+
+/* ---- single clip through the reference's pull callback (signal_t::get_data with
+ * EIDSP_SIGNAL_C_FN_POINTER=1, numpy_types.h:242-249).  Used by the drop-in run_classifier(). --- */
+typedef int (*eikws_get_data_fn)(size_t offset, size_t length, float *out_ptr);
+int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *values,
+                                int *timing_dsp_ms, int *timing_classification_ms);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+const char *eikws_last_error(void); /* thread-local text of the last failure */
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim) */
+uint64_t eikws_launch_count(const eikws_handle *h);
+/* deterministic synthetic int16 clips written on the device (bench/test input generator);
+ * clip c of the stream is generated for index first_clip + c. */
+int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIKWS_B200_H */

@@ -1,0 +1,62 @@
+/* TEST INFRASTRUCTURE ONLY -- see kws_oracle.c.  Not part of the product; the product
+ * (ei-keyword-spotting_b200/) must never include, link or dlopen anything from oracle/. */
+#ifndef KWS_ORACLE_H
+#define KWS_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors ei_dsp_config_mfcc_t (model-parameters/model_metadata.h:92-104) plus the
+ * sample rate (EI_CLASSIFIER_FREQUENCY, model_metadata.h:48). */
+typedef struct {
+    int num_cepstral;
+    float frame_length;
+    float frame_stride;
+    int num_filters;
+    int fft_length;
+    int win_size;
+    int low_frequency;
+    int high_frequency; /* 0 => sample_rate/2 (feature.hpp:203-205) */
+    float pre_cof;
+    int pre_shift;
+    int sample_rate;
+} kws_mfcc_cfg;
+
+/* optional stage taps; any pointer may be NULL */
+typedef struct {
+    float *filterbank; /* [(fft/2+1) x num_filters] transposed, as mfe() holds it          */
+    float *power;      /* [frames x (fft/2+1)]  power spectrum                            */
+    float *energy;     /* [frames]                                                        */
+    float *mel;        /* [frames x num_filters] after zero handling, before log          */
+    float *mfcc;       /* [frames x num_cepstral] before CMVN                             */
+} kws_mfcc_taps;
+
+int kws_oracle_num_frames(const kws_mfcc_cfg *c, int n_samples);
+/* x: float samples as the signal_t callback would return them */
+int kws_oracle_mfcc_f32(const kws_mfcc_cfg *c, const float *x, int n, float *features, kws_mfcc_taps *taps);
+/* pcm: int16, converted exactly like numpy::int16_to_float (numpy.hpp:1289-1298) */
+int kws_oracle_mfcc_i16(const kws_mfcc_cfg *c, const int16_t *pcm, int n, float *features, kws_mfcc_taps *taps);
+
+/* ---- classifier (model container = the raw graph written by tools/ingest) ---- */
+typedef struct kws_model kws_model;
+kws_model *kws_model_load(const void *blob, size_t bytes); /* NULL on parse error */
+void kws_model_free(kws_model *m);
+int kws_model_num_labels(const kws_model *m);
+int kws_model_num_features(const kws_model *m);
+int kws_model_num_tensors(const kws_model *m);
+const kws_mfcc_cfg *kws_model_mfcc_cfg(const kws_model *m);
+const char *kws_model_label(const kws_model *m, int i);
+/* run_inference (ei_run_classifier.h:341-493): features -> probs; optional copy of every
+ * tensor's bytes after invoke (tensor_out[i] may be NULL; sized by kws_model_tensor_bytes). */
+int kws_oracle_run_inference(const kws_model *m, const float *features, float *probs, void **tensor_out);
+int kws_model_tensor_bytes(const kws_model *m, int i);
+/* run_classifier (ei_run_classifier.h:650-714) on int16 PCM */
+int kws_oracle_run_classifier_i16(const kws_model *m, const int16_t *pcm, int n, float *probs, float *features_out);
+int kws_oracle_run_classifier_f32(const kws_model *m, const float *x, int n, float *probs, float *features_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
