@@ -1,0 +1,216 @@
+"""eikws-b200: Python mirror of the reference's classifier interface over libeikws_b200.so (ctypes).
+
+The product is the C-ABI shared library (include/eikws_b200.h); this module is plumbing for tests, bench.py and
+Python callers: it only marshals pointers.  It deliberately has NO fallback: if the CUDA library is missing or no
+B200 is present, construction raises.
+
+Names follow the reference (edge-impulse-sdk/classifier/ei_run_classifier.h): `run_classifier` (:650),
+`run_inference` (:293), `extract_mfcc_features` (ei_run_dsp.h:256); batch arguments replace signal_t.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeikws_b200.so")
+MODELS_DIR = os.path.join(_HERE, "models")
+MODELS = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl"}
+
+EI_IMPULSE_OK = 0
+EI_IMPULSE_DSP_ERROR = -5
+N_SAMPLES = 16000
+
+
+class EikwsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"eikws error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    L.eikws_last_error.restype = C.c_char_p
+    L.eikws_create.argtypes = [C.c_char_p, sz, i32, C.POINTER(vp)]
+    L.eikws_destroy.argtypes = [vp]
+    L.eikws_label.restype = C.c_char_p
+    L.eikws_label.argtypes = [vp, i32]
+    for f in ("eikws_label_count", "eikws_feature_count", "eikws_raw_sample_count", "eikws_device"):
+        getattr(L, f).argtypes = [vp]
+    L.eikws_launch_count.restype = u64
+    L.eikws_launch_count.argtypes = [vp]
+    L.eikws_set_ctas_per_sm.argtypes = [vp, i32]
+    L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
+    L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
+    L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.eikws_features_f32_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.eikws_infer_device.argtypes = [vp, vp, sz, vp, vp]
+    L.eikws_classify_taps_i16_device.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+    L.eikws_synth_i16_device.argtypes = [vp, vp, sz, u64, u64, vp]
+    L.eikws_classify_i16_host.argtypes = [vp, vp, sz, vp]
+    L.eikws_classify_f32_host.argtypes = [vp, vp, sz, vp]
+    L.eikws_features_i16_host.argtypes = [vp, vp, sz, vp, vp]
+    L.eikws_features_f32_host.argtypes = [vp, vp, sz, vp, vp]
+    L.eikws_infer_host.argtypes = [vp, vp, sz, vp]
+    L.eikws_classify_taps_i16_host.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.eikws_debug_host_plan.argtypes = [C.c_char_p, sz, vp, vp, vp, i32, C.POINTER(i32)]
+    _lib = L
+    return L
+
+
+def model_blob(name_or_path: str) -> bytes:
+    path = os.path.join(MODELS_DIR, MODELS[name_or_path]) if name_or_path in MODELS else name_or_path
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def _check(rc):
+    if rc != 0:
+        raise EikwsError(rc, load_library().eikws_last_error().decode(errors="replace"))
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Impulse:
+    """One Edge Impulse impulse (MFCC block + int8 classifier) resident on one B200."""
+
+    def __init__(self, model="l476", device=0):
+        self._lib = load_library()
+        self._blob = model_blob(model) if isinstance(model, str) else bytes(model)
+        h = C.c_void_p()
+        _check(self._lib.eikws_create(self._blob, len(self._blob), int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.label_count = self._lib.eikws_label_count(h)
+        self.feature_count = self._lib.eikws_feature_count(h)
+        self.raw_sample_count = self._lib.eikws_raw_sample_count(h)
+        self.labels = [self._lib.eikws_label(h, i).decode() for i in range(self.label_count)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.eikws_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.eikws_launch_count(self._h))
+
+    def set_ctas_per_sm(self, n: int):
+        _check(self._lib.eikws_set_ctas_per_sm(self._h, n))
+
+    # ---- host (numpy) batch API: H2D + kernel + D2H inside the call -----------------------------------
+    def run_classifier(self, clips: np.ndarray) -> np.ndarray:
+        """clips: [n, 16000] int16 PCM or float32 samples -> [n, label_count] float32 (classification[i].value)."""
+        clips = np.ascontiguousarray(clips).reshape(-1, self.raw_sample_count)
+        out = np.empty((clips.shape[0], self.label_count), np.float32)
+        if clips.dtype == np.int16:
+            _check(self._lib.eikws_classify_i16_host(self._h, _np_ptr(clips), clips.shape[0], _np_ptr(out)))
+        elif clips.dtype == np.float32:
+            _check(self._lib.eikws_classify_f32_host(self._h, _np_ptr(clips), clips.shape[0], _np_ptr(out)))
+        else:
+            raise TypeError("clips must be int16 or float32")
+        return out
+
+    def run_classifier_taps(self, clips: np.ndarray):
+        """int16 clips -> (probs, float features [n,637], int8 quantised NN input [n,637])."""
+        clips = np.ascontiguousarray(clips, dtype=np.int16).reshape(-1, self.raw_sample_count)
+        n = clips.shape[0]
+        probs = np.empty((n, self.label_count), np.float32)
+        feat = np.empty((n, self.feature_count), np.float32)
+        q = np.empty((n, self.feature_count), np.int8)
+        _check(self._lib.eikws_classify_taps_i16_host(self._h, _np_ptr(clips), n, _np_ptr(probs), _np_ptr(feat), _np_ptr(q)))
+        return probs, feat, q
+
+    def extract_mfcc_features(self, clips: np.ndarray, quantized=False):
+        clips = np.ascontiguousarray(clips).reshape(-1, self.raw_sample_count)
+        n = clips.shape[0]
+        feat = np.empty((n, self.feature_count), np.float32)
+        q = np.empty((n, self.feature_count), np.int8) if quantized else None
+        fn = self._lib.eikws_features_i16_host if clips.dtype == np.int16 else self._lib.eikws_features_f32_host
+        if clips.dtype not in (np.int16, np.float32):
+            raise TypeError("clips must be int16 or float32")
+        _check(fn(self._h, _np_ptr(clips), n, _np_ptr(feat), _np_ptr(q) if quantized else None))
+        return (feat, q) if quantized else feat
+
+    def run_inference(self, features: np.ndarray) -> np.ndarray:
+        features = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, self.feature_count)
+        out = np.empty((features.shape[0], self.label_count), np.float32)
+        _check(self._lib.eikws_infer_host(self._h, _np_ptr(features), features.shape[0], _np_ptr(out)))
+        return out
+
+    # ---- device (torch) batch API: tensors already resident in HBM, asynchronous on the current stream -----
+    def run_classifier_device(self, clips, out=None):
+        import torch
+        assert clips.is_cuda and clips.is_contiguous() and clips.device.index == self.device
+        n = clips.numel() // self.raw_sample_count
+        if out is None:
+            out = torch.empty((n, self.label_count), dtype=torch.float32, device=clips.device)
+        stream = C.c_void_p(torch.cuda.current_stream(clips.device).cuda_stream)
+        if clips.dtype == torch.int16:
+            _check(self._lib.eikws_classify_i16_device(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(out.data_ptr()), stream))
+        elif clips.dtype == torch.float32:
+            _check(self._lib.eikws_classify_f32_device(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(out.data_ptr()), stream))
+        else:
+            raise TypeError("clips must be int16 or float32")
+        return out
+
+    def extract_mfcc_features_device(self, clips, features=None, qfeatures=None):
+        import torch
+        assert clips.is_cuda and clips.is_contiguous() and clips.device.index == self.device
+        n = clips.numel() // self.raw_sample_count
+        if features is None and qfeatures is None:
+            features = torch.empty((n, self.feature_count), dtype=torch.float32, device=clips.device)
+        stream = C.c_void_p(torch.cuda.current_stream(clips.device).cuda_stream)
+        fn = self._lib.eikws_features_i16_device if clips.dtype == torch.int16 else self._lib.eikws_features_f32_device
+        _check(fn(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(features.data_ptr()) if features is not None else None,
+                  C.c_void_p(qfeatures.data_ptr()) if qfeatures is not None else None, stream))
+        return features if qfeatures is None else (features, qfeatures)
+
+    def run_inference_device(self, features, out=None):
+        import torch
+        assert features.is_cuda and features.is_contiguous() and features.dtype == torch.float32
+        n = features.numel() // self.feature_count
+        if out is None:
+            out = torch.empty((n, self.label_count), dtype=torch.float32, device=features.device)
+        stream = C.c_void_p(torch.cuda.current_stream(features.device).cuda_stream)
+        _check(self._lib.eikws_infer_device(self._h, C.c_void_p(features.data_ptr()), n, C.c_void_p(out.data_ptr()), stream))
+        return out
+
+    def synth_clips_device(self, n_clips, first_clip=0, seed=0xE1D5):
+        import torch
+        out = torch.empty((n_clips, self.raw_sample_count), dtype=torch.int16, device=f"cuda:{self.device}")
+        stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
+        _check(self._lib.eikws_synth_i16_device(self._h, C.c_void_p(out.data_ptr()), n_clips, first_clip, seed, stream))
+        return out
+
+
+def debug_host_plan(model="l476"):
+    """Host-side derived tables (no GPU needed): dense mel filterbank [129,32] and the conv/FC requantisation
+    multipliers/shifts, for parity tests against the oracle."""
+    L = load_library()
+    blob = model_blob(model) if isinstance(model, str) else bytes(model)
+    fb = np.zeros((129, 32), np.float32)
+    mult = np.zeros(256, np.int32)
+    shift = np.zeros(256, np.int32)
+    n = C.c_int(0)
+    _check(L.eikws_debug_host_plan(blob, len(blob), _np_ptr(fb), _np_ptr(mult), _np_ptr(shift), 256, C.byref(n)))
+    return fb, mult[: n.value].copy(), shift[: n.value].copy()

@@ -85,7 +85,7 @@ int grid_for(const eikws_handle *h, size_t n_clips) {
 }
 
 int launch(eikws_handle *h, const void *clips, bool f32, const float *features_in, size_t n, bool run_nn, float *probs,
-           float *feat, int8_t *qfeat, cudaStream_t st) {
+           float *feat, int8_t *qfeat, cudaStream_t st, float *dbg = nullptr) {
     if (n == 0) return EIKWS_OK;
     if (clips && (reinterpret_cast<uintptr_t>(clips) & 15)) return fail(EIKWS_ERR_BAD_ARG, "clip buffer must be 16-byte aligned (TMA bulk copy)");
     LaunchArgs a;
@@ -98,6 +98,7 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.probs = probs;
     a.features_out = feat;
     a.qfeatures_out = qfeat;
+    a.debug_taps = dbg;
     a.grid = grid_for(h, n);
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
     a.stream = st;
@@ -344,6 +345,29 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
     // the fused kernel does DSP and classification in one launch; the whole latency is reported as dsp
     if (t_dsp_ms) *t_dsp_ms = static_cast<int>(std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
     if (t_cls_ms) *t_cls_ms = 0;
+    return rc;
+}
+
+// stage taps of the fused kernel for parity debugging (tests only): per clip P[129][49] (transposed power spectra),
+// log-mel [49][33], pre-CMVN cepstra [49][13]; returns the record length through *floats_per_clip when taps == NULL
+int eikws_debug_stage_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *taps, int *floats_per_clip) {
+    if (floats_per_clip) *floats_per_clip = debug_tap_floats();
+    if (!taps) return EIKWS_OK;
+    if (!h || !pcm) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    int rc;
+    cudaError_t e;
+    const size_t L = h->graph.labels.size(), rec = static_cast<size_t>(debug_tap_floats());
+    if ((rc = ensure(&h->d_in, &h->d_in_bytes, n * kSamples * 2))) return rc;
+    if ((rc = ensure(reinterpret_cast<void **>(&h->d_probs), &h->d_probs_bytes, n * L * 4))) return rc;
+    float *d_taps = nullptr;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&d_taps), n * rec * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(taps)");
+    if ((e = cudaMemcpyAsync(h->d_in, pcm, n * kSamples * 2, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return cuda_fail(e, "H2D");
+    rc = launch(h, h->d_in, false, nullptr, n, true, h->d_probs, nullptr, nullptr, h->stream, d_taps);
+    if (!rc && (e = cudaMemcpyAsync(taps, d_taps, n * rec * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) rc = cuda_fail(e, "D2H");
+    if (!rc && (e = cudaStreamSynchronize(h->stream)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
+    cudaFree(d_taps);
     return rc;
 }
 

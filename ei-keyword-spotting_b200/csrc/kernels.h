@@ -19,6 +19,7 @@ struct LaunchArgs {
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
+    float *debug_taps = nullptr;         // device, tests only: [n_clips][debug_tap_floats()] (int16 classify path)
     int grid = 0;
     int nn_smem_bytes = 0;               // activation arena + conv row scratch
     cudaStream_t stream = nullptr;
@@ -27,6 +28,7 @@ struct LaunchArgs {
 cudaError_t launch_run_classifier(const LaunchArgs &a);
 cudaError_t launch_synth(int16_t *pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, cudaStream_t st);
 int kernel_threads();
+int debug_tap_floats();  // P[129][49] + logmel[49][33] + cepstra[49][13]
 // bytes of shared memory available to the classifier arena inside the fused kernel's overlay
 int nn_smem_capacity(bool input_is_f32);
 

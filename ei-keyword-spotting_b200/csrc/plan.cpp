@@ -16,6 +16,16 @@
 namespace eikws {
 namespace {
 
+// libm entry points reached through volatile function pointers.  The tables below must hold exactly what the
+// reference computes AT RUN TIME with the C library (kiss_fft_alloc, fast-dct-fft.cpp:71-74, functions.hpp:52-54);
+// with compile-time-constant geometry GCC would otherwise fold cosf/sinf through MPFR (correctly rounded), which
+// differs from glibc's results by one ulp for some arguments (seen: cosf/sinf(i*pi/64), i = 6 and 11).
+float (*volatile rt_cosf)(float) = cosf;
+float (*volatile rt_sinf)(float) = sinf;
+float (*volatile rt_expf)(float) = expf;
+double (*volatile rt_cos)(double) = cos;
+double (*volatile rt_sin)(double) = sin;
+
 struct Fixup {
     size_t field_off;  // byte offset of the pointer member inside DevPlan
     size_t blob_off;
@@ -75,7 +85,7 @@ void mel_filterbank(std::vector<float> &fb, int filters, int bins, uint32_t fs, 
     auto to_mel = [](float f) { return static_cast<float>(1127.0 * static_cast<double>(fastlog_host(1 + f / 700.0f))); };
     linspace(to_mel(static_cast<float>(low)), to_mel(static_cast<float>(high)), n, mels.data());
     for (int i = 0; i < n; i++) {
-        hz[i] = 700.0f * (std::exp(mels[i] / 1127.0f) - 1.0f);  // float overload == expf
+        hz[i] = 700.0f * (rt_expf(mels[i] / 1127.0f) - 1.0f);
         if (hz[i] < static_cast<float>(low)) hz[i] = static_cast<float>(low);
         if (hz[i] > static_cast<float>(high)) hz[i] = static_cast<float>(high);
         if (i == n - 1) hz[i] = static_cast<float>(static_cast<double>(hz[i]) - 0.001);
@@ -100,14 +110,14 @@ void fft_twiddles(int nfft, std::vector<float2> &tw) {  // kiss_fft_alloc (kiss_
     for (int i = 0; i < nfft; i++) {
         const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
         double phase = -2 * pi * i / nfft;
-        tw[i] = make_float2(static_cast<float>(std::cos(phase)), static_cast<float>(std::sin(phase)));
+        tw[i] = make_float2(static_cast<float>(rt_cos(phase)), static_cast<float>(rt_sin(phase)));
     }
 }
 void super_twiddles(int ncfft, std::vector<float2> &stw) {  // kiss_fftr_alloc (kiss_fftr.cpp:51-57)
     stw.resize(ncfft / 2);
     for (int i = 0; i < ncfft / 2; i++) {
         double phase = -3.14159265358979323846264338327 * (static_cast<double>(i + 1) / ncfft + .5);
-        stw[i] = make_float2(static_cast<float>(std::cos(phase)), static_cast<float>(std::sin(phase)));
+        stw[i] = make_float2(static_cast<float>(rt_cos(phase)), static_cast<float>(rt_sin(phase)));
     }
 }
 
@@ -242,7 +252,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
     for (int i = 0; i < kFilters / 2 + 1; i++) {
         // fast-dct-fft.cpp:71-74: float temp = i * M_PI / (len * 2); cos(temp)/sin(temp) resolve to the float overloads
         float temp = static_cast<float>(static_cast<double>(i) * 3.14159265358979323846264338327950288 / static_cast<double>(kFilters * 2));
-        dcs[i] = make_float2(std::cos(temp), std::sin(temp));
+        dcs[i] = make_float2(rt_cosf(temp), rt_sinf(temp));
     }
     std::vector<uint8_t> psrc;
     pad_rows(kFrames, kPad, kPad, psrc);

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/liboracle_ref_<model>.so, built by
+`make -C oracle ref` from /root/reference).  Run in the build container only; the GPU box has no reference and
+uses the committed files.  The reference ships no golden vectors of its own, so these are the
+pinned known answers for every layer of the test pyramid.
+
+Inputs are not stored: they are regenerated from (seed, index) by ei-keyword-spotting_b200/synth.py, except the
+hand-built special clips whose names are recorded.  Stored per model:
+  features   [n,637] float32  extract_mfcc_features output (bit pattern matters)
+  probs      [n,L]   float32  run_classifier output
+  mel0/energy0/mfcc0          stage taps of clip 0 (mfe output, frame energies, pre-CMVN cepstra)
+  filterbank [129,32]
+  nn_features [m,637], nn_probs [m,L], nn_t19/21/23/25/27/29/30: run_inference on crafted feature vectors and the
+  TFLite tensors that are still intact in the arena after invoke (see tests/test_oracle.py for the byte ranges)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import eikws_pkg  # noqa: E402
+
+eikws_pkg.load()
+import eikws_b200.synth as synth  # noqa: E402
+from oracle_lib import RefOracle  # noqa: E402
+
+N_SYNTH = 40
+GOLDEN_SEED = 0xE1D5
+INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}  # + output-sized 29, 30
+
+
+def crafted_features(n_labels_seed: int) -> np.ndarray:
+    rng = np.random.default_rng(1234 + n_labels_seed)
+    F = rng.normal(0, 1.5, (96, 637)).astype(np.float32)
+    F[24:48] *= 4                                                      # saturates int8
+    F[48:64] = rng.uniform(-300, 300, (16, 637)).astype(np.float32)    # wraps the float->int8 cast
+    odd = np.array([1e6, -1e6, 1.4e7, -1.4e7, 2e9, -2e9, 5e9, -5e9, 1e20, -1e20, np.inf, -np.inf, np.nan, 0.0, -0.0], np.float32)
+    F[64:72] = rng.choice(odd, (8, 637))
+    F[72:96] = rng.normal(0, 0.3, (24, 637)).astype(np.float32)
+    return F
+
+
+def main():
+    for mi, name in enumerate(("l476", "l432")):
+        ref = RefOracle(name)
+        specials = synth.special_clips()
+        clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values()))])
+        feats = ref.mfcc_i16(clips)
+        probs = ref.run_classifier_i16(clips)
+        mel0, en0 = ref.mfe_i16(clips[0])
+        mfcc0 = ref.mfcc_nocmvn_i16(clips[0])
+        # float-input path (config 5 style signal): same clips scaled as the demo callback would
+        xf = (clips[:8].astype(np.float32) / np.float32(32768))
+        feats_f32 = ref.mfcc_f32(xf)
+        F = crafted_features(mi)
+        nn_probs, tens = ref.run_inference(F, want_tensors=True)
+        out = dict(n_synth=N_SYNTH, seed=GOLDEN_SEED, special_names=np.array(list(specials.keys())),
+                   features=feats, probs=probs, mel0=mel0, energy0=en0, mfcc0=mfcc0, filterbank=ref.filterbank(),
+                   features_f32in=feats_f32, nn_features=F, nn_probs=nn_probs, labels=np.array(ref.labels))
+        n_t = len(tens[0])
+        for k, (lo, hi) in INTACT.items():
+            out[f"nn_t{k}"] = np.stack([t[k][lo:hi] for t in tens])
+        out["nn_t_fc"] = np.stack([t[n_t - 2] for t in tens])
+        out["nn_t_out"] = np.stack([t[n_t - 1] for t in tens])
+        path = os.path.join(HERE, f"golden_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path), "bytes;", "argmax histogram", np.bincount(probs.argmax(1), minlength=ref.n_labels))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,165 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (libeikws_b200.so), against
+(a) the golden vectors generated from the unmodified reference and (b) the plain-C oracle on fresh seeded inputs.
+Bar: bit-exact int8 classifier outputs AND bit-identical float MFCC features (north star asks 1e-5; we hold 0)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import PortOracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = ("l476", "l432")
+FEATURE_TOL = 1e-5  # north-star tolerance on the float MFCC coefficients (we additionally assert exact equality)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))
+
+
+def golden_clips(synth, g):
+    sp = synth.special_clips()
+    return np.concatenate([synth.synth_clips(int(g["n_synth"]), 0, int(g["seed"])), np.stack([sp[str(k)] for k in g["special_names"]])])
+
+
+def same_floats(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+
+
+@pytest.fixture(scope="module")
+def impulses(eikws):
+    d = {m: eikws.Impulse(m, device=0) for m in MODELS}
+    yield d
+    for v in d.values():
+        v.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_run_classifier_matches_reference_golden(name, impulses, synth):
+    g = golden(name)
+    imp = impulses[name]
+    assert imp.labels == [str(s) for s in g["labels"]]
+    clips = golden_clips(synth, g)
+    probs, feats, q = imp.run_classifier_taps(clips)
+    assert np.nanmax(np.abs(feats - g["features"])) <= FEATURE_TOL
+    bad = np.where(~((feats == g["features"]) | (np.isnan(feats) & np.isnan(g["features"]))).all(axis=1))[0]
+    assert bad.size == 0, f"clips with non-identical features: {bad[:10]}"
+    assert np.array_equal(probs, g["probs"])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_features_only_and_float_input(name, impulses, synth):
+    g = golden(name)
+    imp = impulses[name]
+    clips = golden_clips(synth, g)
+    feats = imp.extract_mfcc_features(clips)
+    assert same_floats(feats, g["features"])
+    x = clips[:8].astype(np.float32) / np.float32(32768)
+    assert same_floats(imp.extract_mfcc_features(x), g["features_f32in"])
+    assert np.array_equal(imp.run_classifier(x), g["probs"][:8])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_int8_classifier_matches_reference_golden(name, impulses):
+    """run_inference alone on crafted feature vectors (saturating, wrapping the float->int8 cast, inf/nan)"""
+    g = golden(name)
+    probs = impulses[name].run_inference(g["nn_features"])
+    assert np.array_equal(probs, g["nn_probs"])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_quantised_input_matches_oracle(name, impulses, synth):
+    g = golden(name)
+    imp = impulses[name]
+    clips = golden_clips(synth, g)
+    _, q = imp.extract_mfcc_features(clips, quantized=True)
+    port = PortOracle(name)
+    _, tens = port.run_inference(g["features"], want_tensors=True)
+    want = np.stack([t[0] for t in tens]).view(np.int8)  # tensor 0 = quantised NN input
+    assert np.array_equal(q, want)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_fresh_clips_against_plain_c_oracle(name, impulses, synth):
+    imp = impulses[name]
+    port = PortOracle(name)
+    clips = synth.synth_clips(256, first_clip=5000, seed=0xC0FFEE)
+    probs, feats, _ = imp.run_classifier_taps(clips)
+    want_p, want_f = port.run_classifier_i16(clips, want_features=True)
+    assert same_floats(feats, want_f)
+    assert np.array_equal(probs, want_p)
+
+
+def test_device_path_equals_host_path_and_synth_twin(impulses, synth):
+    import torch
+    imp = impulses["l476"]
+    n = 1000  # not a multiple of the grid: exercises the ragged tail of the persistent loop
+    d_clips = imp.synth_clips_device(n, first_clip=123, seed=0xE1D5)
+    torch.cuda.synchronize()
+    h_clips = d_clips.cpu().numpy()
+    assert np.array_equal(h_clips[:64], synth.synth_clips(64, first_clip=123, seed=0xE1D5))
+    d_probs = imp.run_classifier_device(d_clips)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_probs.cpu().numpy(), imp.run_classifier(h_clips))
+    feats = imp.extract_mfcc_features_device(d_clips)
+    d_probs2 = imp.run_inference_device(feats)
+    torch.cuda.synchronize()
+    assert torch.equal(d_probs, d_probs2)  # fused == MFCC kernel + inference kernel
+
+
+def test_batch_properties_at_full_size(impulses, synth):
+    """BASELINE config 2 size (65,536 clips): size-independent properties -- permutation/sharding invariance
+    (a clip's result does not depend on its position or on its neighbours), duplicates agree, probabilities are
+    valid int8-softmax outputs, and a subsample agrees with the oracle."""
+    import torch
+    imp = impulses["l476"]
+    n = 65536
+    d = imp.synth_clips_device(n, first_clip=0, seed=0xE1D5)
+    p = imp.run_classifier_device(d)
+    torch.cuda.synchronize()
+    # sharded 8 ways (what 8 GPUs would each see) == unsharded
+    shard = n // 8
+    for s in (0, 3, 7):
+        ps = imp.run_classifier_device(d[s * shard:(s + 1) * shard].contiguous())
+        assert torch.equal(ps, p[s * shard:(s + 1) * shard])
+    perm = torch.randperm(n, device=d.device, generator=torch.Generator(device=d.device).manual_seed(1))
+    pp = imp.run_classifier_device(d[perm].contiguous())
+    assert torch.equal(pp, p[perm])
+    ph = p.cpu().numpy()
+    assert np.all((ph >= 0) & (ph <= 255 / 256)) and np.all(ph * 256 == np.round(ph * 256))
+    assert np.all(np.abs(ph.sum(axis=1) - 1.0) <= 4 / 256 + 1e-6)
+    idx = np.arange(0, n, 1024)
+    port = PortOracle("l476")
+    assert np.array_equal(ph[idx], port.run_classifier_i16(d[torch.from_numpy(idx).to(d.device)].cpu().numpy()))
+
+
+def test_error_behaviour(eikws, impulses):
+    import torch
+    imp = impulses["l476"]
+    lib = eikws.load_library()
+    d = torch.zeros(16000 * 2 + 8, dtype=torch.int16, device="cuda:0")
+    out = torch.zeros(4, dtype=torch.float32, device="cuda:0")
+    # misaligned clip pointer: refused (TMA bulk copies need 16-byte alignment), nothing launched
+    rc = lib.eikws_classify_i16_device(imp._h, C.c_void_p(d.data_ptr() + 2), 1, C.c_void_p(out.data_ptr()), None)
+    assert rc == -102
+    # empty batch is a no-op
+    assert lib.eikws_classify_i16_device(imp._h, C.c_void_p(d.data_ptr()), 0, C.c_void_p(out.data_ptr()), None) == 0
+    # single-clip pull API: wrong signal length -> EI_IMPULSE_DSP_ERROR like ei_run_dsp.h:279-283
+    CB = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_float))
+
+    def get_data(off, length, outp):
+        for i in range(length):
+            outp[i] = 0.0
+        return 0
+
+    vals = (C.c_float * 4)()
+    lib.eikws_run_classifier_signal.argtypes = [C.c_void_p, CB, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    assert lib.eikws_run_classifier_signal(imp._h, CB(get_data), 16320, vals, None, None) == -5
+    assert lib.eikws_run_classifier_signal(imp._h, CB(get_data), 16000, vals, None, None) == 0
+    g = golden("l476")
+    sil = [str(k) for k in g["special_names"]].index("silence") + int(g["n_synth"])
+    assert np.array_equal(np.array(vals[:], np.float32), g["probs"][sil])

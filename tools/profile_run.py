@@ -1,0 +1,20 @@
+"""Small driver for ncu captures: runs the fused kernel a few times over a device-resident synthetic batch."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import eikws_pkg
+
+m = eikws_pkg.load()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+imp = m.Impulse("l476")
+clips = imp.synth_clips_device(n)
+out = torch.empty((n, imp.label_count), dtype=torch.float32, device="cuda:0")
+for _ in range(reps):
+    imp.run_classifier_device(clips, out=out)
+torch.cuda.synchronize()
+print("done", out[:2].tolist())
