@@ -348,6 +348,21 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
     return rc;
 }
 
+int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *features) {
+    if (!h || !get_data || !features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard guard(h->device);
+        if (!h->h_pinned) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        }
+    }
+    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
+    return eikws_features_f32_host(h, h->h_pinned, 1, features, nullptr);
+}
+
 // stage taps of the fused kernel for parity debugging (tests only): per clip P[129][49] (transposed power spectra),
 // log-mel [49][33], pre-CMVN cepstra [49][13]; returns the record length through *floats_per_clip when taps == NULL
 int eikws_debug_stage_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *taps, int *floats_per_clip) {

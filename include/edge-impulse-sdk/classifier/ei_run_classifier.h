@@ -1,0 +1,219 @@
+/* eikws-b200 drop-in for edge-impulse-sdk/classifier/ei_run_classifier.h
+ *
+ * Same include path, same entry points, same types as the reference header
+ *   run_classifier(signal_t*, ei_impulse_result_t*, bool debug = false)      reference :650-714
+ *   run_inference(ei::matrix_t*, ei_impulse_result_t*, bool debug = false)   reference :293-641
+ *   run_classifier_init()                                                    reference :164-172
+ * but the work is done by libeikws_b200.so on a B200: the MFCC block and the int8 classifier run as one fused
+ * sm_100a kernel.  The application keeps its UNMODIFIED generated files
+ *   model-parameters/model_metadata.h, model-parameters/dsp_blocks.h, tflite-model/trained_model_compiled.{h,cpp}
+ * and replaces the `edge-impulse-sdk/` directory by this repo's include/edge-impulse-sdk.
+ * On the first call the generated trained_model_init() is executed once against the library's recording
+ * Register_*() operators (tensorflow/lite/micro/kernels/micro_ops.h) and the captured graph is lowered to a
+ * device plan; nothing is recomputed per call (the reference re-inits the model on every call, :352/:487).
+ *
+ * Batch extension (one callback per clip cannot feed a GPU): run_classifier_batch_i16 / _f32 below, and the
+ * C ABI in eikws_b200.h.  Environment: EIKWS_DEVICE selects the CUDA device (default 0).
+ */
+#ifndef _EDGE_IMPULSE_RUN_CLASSIFIER_H_
+#define _EDGE_IMPULSE_RUN_CLASSIFIER_H_
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "model-parameters/model_metadata.h"
+
+#include "../dsp/numpy_types.h"
+#include "../porting/ei_classifier_porting.h"
+#include "ei_classifier_types.h"
+#include "ei_model_types.h"
+#include "ei_run_dsp.h"
+#include "eikws_b200.h"
+#include "model-parameters/dsp_blocks.h"
+#include "tflite-model/trained_model_compiled.h"
+
+#if EI_CLASSIFIER_INFERENCING_ENGINE != EI_CLASSIFIER_TFLITE || EI_CLASSIFIER_COMPILED != 1
+#error "eikws-b200 accelerates EON-compiled TFLite impulses (EI_CLASSIFIER_INFERENCING_ENGINE == EI_CLASSIFIER_TFLITE, EI_CLASSIFIER_COMPILED == 1)"
+#endif
+
+#ifdef __cplusplus
+using ei::matrix_t;
+using ei::signal_t;
+
+namespace {
+
+static int eikws_dropin_init_thunk(void *(*a)(size_t, size_t)) { return (int)trained_model_init(a); }
+static void *eikws_dropin_input_thunk(int i) { return trained_model_input(i); }
+static void *eikws_dropin_output_thunk(int i) { return trained_model_output(i); }
+static int eikws_dropin_reset_thunk(void (*f)(void *)) { return (int)trained_model_reset(f); }
+
+/* Lowers the impulse on first use; returns NULL (after printing the reason) when that fails. */
+static eikws_handle *eikws_dropin_handle() {
+    static eikws_handle *handle = NULL;
+    static bool tried = false;
+    if (tried) return handle;
+    tried = true;
+    if (ei_dsp_blocks_size != 1) {
+        ei_printf("ERR: eikws-b200 supports impulses with exactly one (MFCC) DSP block\n");
+        return NULL;
+    }
+    const ei_dsp_config_mfcc_t *c = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
+    eikws_compiled_model_t cm;
+    cm.init = eikws_dropin_init_thunk;
+    cm.input = eikws_dropin_input_thunk;
+    cm.output = eikws_dropin_output_thunk;
+    cm.reset = eikws_dropin_reset_thunk;
+    cm.raw_sample_count = EI_CLASSIFIER_RAW_SAMPLE_COUNT;
+    cm.nn_input_frame_size = EI_CLASSIFIER_NN_INPUT_FRAME_SIZE;
+    cm.label_count = EI_CLASSIFIER_LABEL_COUNT;
+    cm.frequency = EI_CLASSIFIER_FREQUENCY;
+    cm.labels = ei_classifier_inferencing_categories;
+    cm.mfcc_num_cepstral = c->num_cepstral;
+    cm.mfcc_frame_length = c->frame_length;
+    cm.mfcc_frame_stride = c->frame_stride;
+    cm.mfcc_num_filters = c->num_filters;
+    cm.mfcc_fft_length = c->fft_length;
+    cm.mfcc_win_size = c->win_size;
+    cm.mfcc_low_frequency = c->low_frequency;
+    cm.mfcc_high_frequency = c->high_frequency;
+    cm.mfcc_pre_cof = c->pre_cof;
+    cm.mfcc_pre_shift = c->pre_shift;
+    void *blob = NULL;
+    size_t bytes = 0;
+    if (eikws_model_from_compiled(&cm, &blob, &bytes) != EIKWS_OK) {
+        ei_printf("ERR: eikws-b200 could not capture the compiled model: %s\n", eikws_last_error());
+        return NULL;
+    }
+    const char *dev = getenv("EIKWS_DEVICE");
+    int rc = eikws_create(blob, bytes, dev ? atoi(dev) : 0, &handle);
+    eikws_free(blob);
+    if (rc != EIKWS_OK) {
+        ei_printf("ERR: eikws-b200 could not create the device plan (%d): %s\n", rc, eikws_last_error());
+        handle = NULL;
+    }
+    return handle;
+}
+
+/* signal_t::get_data may be a std::function (EIDSP_SIGNAL_C_FN_POINTER == 0, the SDK default); the C ABI takes a
+ * plain function pointer, so the current signal is parked here for the duration of the call. run_classifier is
+ * serialised per process exactly like the reference (which keeps global state, ei_run_dsp.h:251). */
+static signal_t *eikws_dropin_current_signal = NULL;
+static int eikws_dropin_get_data(size_t offset, size_t length, float *out) {
+    return eikws_dropin_current_signal->get_data(offset, length, out);
+}
+
+static EI_IMPULSE_ERROR eikws_dropin_error(int rc) {
+    switch (rc) {
+        case EIKWS_OK: return EI_IMPULSE_OK;
+        case EIKWS_ERR_DSP: return EI_IMPULSE_DSP_ERROR;
+        case EIKWS_ERR_SHAPES_DONT_MATCH: return EI_IMPULSE_ERROR_SHAPES_DONT_MATCH;
+        case EIKWS_ERR_CANCELED: return EI_IMPULSE_CANCELED;
+        case EIKWS_ERR_ALLOC_FAILED: return EI_IMPULSE_ALLOC_FAILED;
+        case EIKWS_ERR_CUDA: return EI_IMPULSE_ALLOC_FAILED;  /* no device / device failure */
+        default: return EI_IMPULSE_TFLITE_ERROR;
+    }
+}
+
+static void eikws_dropin_fill_result(ei_impulse_result_t *result, const float *values, bool debug) {
+    for (uint32_t ix = 0; ix < EI_CLASSIFIER_LABEL_COUNT; ix++) {
+        result->classification[ix].label = ei_classifier_inferencing_categories[ix];
+        result->classification[ix].value = values[ix];
+        if (debug) {
+            ei_printf("%s:\t", ei_classifier_inferencing_categories[ix]);
+            ei_printf_float(values[ix]);
+            ei_printf("\n");
+        }
+    }
+    result->anomaly = 0.0f;
+}
+
+}  // namespace
+
+static int eikws_dropin_extract_mfcc(ei::signal_t *signal, ei::matrix_t *output_matrix) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return -1004; /* EIDSP_OUT_OF_MEM class of failure */
+    if (output_matrix->rows * output_matrix->cols < (uint32_t)EI_CLASSIFIER_NN_INPUT_FRAME_SIZE) return EIDSP_MATRIX_SIZE_MISMATCH;
+    eikws_dropin_current_signal = signal;
+    int rc = eikws_extract_mfcc_signal(h, &eikws_dropin_get_data, signal->total_length, output_matrix->buffer);
+    if (rc != EIKWS_OK) return EIDSP_MATRIX_SIZE_MISMATCH;
+    output_matrix->cols = output_matrix->rows * output_matrix->cols;
+    output_matrix->rows = 1;
+    return EIDSP_OK;
+}
+
+namespace {
+
+/* reference :164-172 -- resets the continuous-mode state; the one-shot path is stateless */
+extern "C" void run_classifier_init(void) {}
+
+/* reference :293-641: classify an already-extracted feature matrix */
+extern "C" EI_IMPULSE_ERROR run_inference(ei::matrix_t *fmatrix, ei_impulse_result_t *result, bool debug = false) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
+    if (fmatrix->rows * fmatrix->cols != (uint32_t)EI_CLASSIFIER_NN_INPUT_FRAME_SIZE) return EI_IMPULSE_ERROR_SHAPES_DONT_MATCH;
+    float values[EI_CLASSIFIER_LABEL_COUNT];
+    uint64_t t0 = ei_read_timer_ms();
+    int rc = eikws_infer_host(h, fmatrix->buffer, 1, values);
+    result->timing.classification = (int)(ei_read_timer_ms() - t0);
+    if (rc != EIKWS_OK) return eikws_dropin_error(rc);
+    if (debug) ei_printf("Predictions (time: %d ms.):\n", result->timing.classification);
+    eikws_dropin_fill_result(result, values, debug);
+    if (ei_run_impulse_check_canceled() == EI_IMPULSE_CANCELED) return EI_IMPULSE_CANCELED;
+    return EI_IMPULSE_OK;
+}
+
+/* reference :650-714 */
+extern "C" EI_IMPULSE_ERROR run_classifier(signal_t *signal, ei_impulse_result_t *result, bool debug = false) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
+    float values[EI_CLASSIFIER_LABEL_COUNT];
+    int t_dsp = 0, t_cls = 0;
+    eikws_dropin_current_signal = signal;
+    int rc = eikws_run_classifier_signal(h, &eikws_dropin_get_data, signal->total_length, values, &t_dsp, &t_cls);
+    if (rc != EIKWS_OK) {
+        if (rc == EIKWS_ERR_DSP) ei_printf("ERR: Failed to run DSP process (%d)\n", rc);
+        return eikws_dropin_error(rc);
+    }
+    result->timing.sampling = 0;
+    result->timing.dsp = t_dsp;
+    result->timing.classification = t_cls;
+    result->timing.anomaly = 0;
+    if (debug) ei_printf("Predictions (DSP+NN fused, time: %d ms.):\n", t_dsp);
+    eikws_dropin_fill_result(result, values, debug);
+    if (ei_run_impulse_check_canceled() == EI_IMPULSE_CANCELED) return EI_IMPULSE_CANCELED;
+    return EI_IMPULSE_OK;
+}
+
+/* ---- batch extension: n_clips contiguous clips of EI_CLASSIFIER_RAW_SAMPLE_COUNT samples (host memory) ---- */
+extern "C" EI_IMPULSE_ERROR run_classifier_batch_i16(const int16_t *pcm, size_t n_clips, ei_impulse_result_t *results) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
+    float *values = (float *)malloc(sizeof(float) * EI_CLASSIFIER_LABEL_COUNT * (n_clips ? n_clips : 1));
+    if (!values) return EI_IMPULSE_ALLOC_FAILED;
+    int rc = eikws_classify_i16_host(h, pcm, n_clips, values);
+    for (size_t i = 0; rc == EIKWS_OK && i < n_clips; i++) {
+        memset(&results[i].timing, 0, sizeof(results[i].timing));
+        eikws_dropin_fill_result(&results[i], values + i * EI_CLASSIFIER_LABEL_COUNT, false);
+    }
+    free(values);
+    return eikws_dropin_error(rc);
+}
+
+extern "C" EI_IMPULSE_ERROR run_classifier_batch_f32(const float *samples, size_t n_clips, ei_impulse_result_t *results) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
+    float *values = (float *)malloc(sizeof(float) * EI_CLASSIFIER_LABEL_COUNT * (n_clips ? n_clips : 1));
+    if (!values) return EI_IMPULSE_ALLOC_FAILED;
+    int rc = eikws_classify_f32_host(h, samples, n_clips, values);
+    for (size_t i = 0; rc == EIKWS_OK && i < n_clips; i++) {
+        memset(&results[i].timing, 0, sizeof(results[i].timing));
+        eikws_dropin_fill_result(&results[i], values + i * EI_CLASSIFIER_LABEL_COUNT, false);
+    }
+    free(values);
+    return eikws_dropin_error(rc);
+}
+
+}  // namespace
+#endif /* __cplusplus */
+#endif /* _EDGE_IMPULSE_RUN_CLASSIFIER_H_ */

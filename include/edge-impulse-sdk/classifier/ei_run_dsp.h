@@ -1,0 +1,20 @@
+/* eikws-b200 drop-in for edge-impulse-sdk/classifier/ei_run_dsp.h: the DSP block entry point whose address the
+ * generated dsp_blocks.h stores (`&extract_mfcc_features`, dsp_blocks.h:33).  Reference: ei_run_dsp.h:256-308.
+ * Here it is a thin call into libeikws_b200.so (the fused MFCC kernel run in features-only mode). */
+#ifndef EIKWS_EI_RUN_DSP_H_
+#define EIKWS_EI_RUN_DSP_H_
+
+#include "../dsp/numpy_types.h"
+#include "eikws_dropin_runtime.h"
+
+#ifndef EIDSP_OK
+#define EIDSP_OK 0
+#define EIDSP_MATRIX_SIZE_MISMATCH (-1002)
+#endif
+
+__attribute__((unused)) static int extract_mfcc_features(ei::signal_t *signal, ei::matrix_t *output_matrix, void *config_ptr) {
+    (void)config_ptr;  // the configuration was captured when the impulse was lowered (eikws_dropin_handle)
+    return eikws_dropin_extract_mfcc(signal, output_matrix);
+}
+
+#endif /* EIKWS_EI_RUN_DSP_H_ */

@@ -113,6 +113,9 @@ typedef int (*eikws_get_data_fn)(size_t offset, size_t length, float *out_ptr);
 int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *values,
                                 int *timing_dsp_ms, int *timing_classification_ms);
 
+/* extract_mfcc_features (ei_run_dsp.h:256-308) for one clip pulled through the same callback: features[feature_count] */
+int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *features);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *eikws_last_error(void); /* thread-local text of the last failure */
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim) */
