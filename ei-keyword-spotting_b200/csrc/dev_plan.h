@@ -67,6 +67,35 @@ struct NnOpDev {
 
 constexpr int kMaxNnOps = 16;
 
+// ---- fused classifier plan (the topology of every model the reference ships) --------------------------------
+// [CONV_2D 1xk, stride 1] -> [ADD constant + ReLU] -> [MAX_POOL over the conv width] , twice, then
+// FULLY_CONNECTED -> SOFTMAX.  Activations live in shared memory as channel-padded rows [pos][cp] (cp multiple of
+// 16 bytes, halo rows and padding lanes pre-filled with the zero point) so that every operand fetch is an aligned
+// 128-bit load and the pooled result is written straight into the next stage's padded input.
+struct NnFusedStage {
+    int32_t in_w, in_c, cp, kw, pad_w, out_c;   // conv geometry; cp = padded channel count (bytes per row)
+    int32_t pool, pool_out;                     // pool window (== stride) along the conv width, pooled positions
+    int32_t in_zp, conv_out_zp, conv_act_min, conv_act_max, pool_act_min, pool_act_max;
+    int32_t in_off, in_rows;                    // padded input buffer: byte offset in the arena, rows = in_w + kw - 1
+    int32_t out_off, out_cp, out_row0, out_rows, out_fill;  // consumer layout: row stride, first interior row, total rows, halo byte
+    const int32_t *weights;  // [out_c][kw][cp/4] packed int8, zero in the padding lanes
+    const int32_t *bias;     // [out_c] bias + in_offset * sum(weights)
+    const int32_t *mult;     // [out_c]
+    const int32_t *shift;    // [out_c]
+    const uint8_t *lut;      // [out_c][256] ADD+activation table over the conv output byte
+};
+
+struct NnFusedDev {
+    int32_t enabled;
+    NnFusedStage st[2];
+    // tail: FULLY_CONNECTED [fc_d] -> [fc_o], SOFTMAX over fc_o
+    int32_t fc_in_off, fc_d, fc_o, fc_in_zp, fc_out_zp, fc_act_min, fc_act_max, fc_mult, fc_shift;
+    int32_t tail_off;        // scratch for the fc output / softmax output bytes
+    const int8_t *fc_w;      // [fc_o][fc_d]
+    const int32_t *fc_bias;  // [fc_o] bias + in_offset * sum(weights)
+    const int32_t *exp_lut;  // [256]
+};
+
 struct NnDev {
     int32_t n_ops;
     int32_t in_off;       // arena offset of the quantised input tensor
@@ -78,6 +107,7 @@ struct NnDev {
     float out_scale;
     int32_t out_zp;
     NnOpDev ops[kMaxNnOps];
+    NnFusedDev fused;
 };
 
 struct DevPlan {

@@ -284,6 +284,16 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
     mf.q_zp = tin.zero_point();
     mf.input_is_int8 = 1;
 
+    // raw material kept aside for the fused plan (see build_fused below)
+    struct ConvSrc {
+        int op_index;
+        const int8_t *w;
+        std::vector<int32_t> raw_bias, mult, shift;
+    };
+    std::vector<ConvSrc> conv_src;
+    std::vector<std::pair<int, std::vector<uint8_t>>> lut_src;
+    std::vector<int32_t> exp_lut_src;
+
     uint32_t max_bytes = 0;
     for (const TensorDesc &t : g.tensors)
         if (!t.is_const && t.bytes > max_bytes) max_bytes = t.bytes;
@@ -400,6 +410,15 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 quantize_multiplier(eff[oc], &mult[oc], &sh);
                 shift[oc] = sh;
             }
+            {
+                ConvSrc cs;
+                cs.op_index = nn.n_ops;
+                cs.w = w;
+                cs.mult = mult;
+                cs.shift = shift;
+                for (int oc = 0; oc < op.out_c; oc++) cs.raw_bias.push_back(bsrc ? bsrc[oc] : 0);
+                conv_src.push_back(std::move(cs));
+            }
             const int lead = op.pad_w * op.in_c, data_bytes = op.in_w * op.in_c;
             int need = (op.out_w - 1) * op.stride_w * op.in_c + 4 * op.k_words + 8;
             if (need < lead + data_bytes) need = lead + data_bytes;
@@ -457,6 +476,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             op.n_elems = static_cast<int32_t>(out.bytes);
             op.n_const = static_cast<int32_t>(cst.bytes);
             b.bind(op.lut, b.push(lut.data(), lut.size()));
+            lut_src.emplace_back(nn.n_ops, lut);
             op.in_off = off[ia];
         } else if (n.op == kOpMaxPool2D) {
             const TensorDesc &in = g.tensors[n.inputs[0]];
@@ -510,6 +530,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             op.kind = kNnSoftmax;
             op.n_elems = in.dims.back();
             b.bind(op.exp_lut, b.push(elut.data(), elut.size() * 4));
+            exp_lut_src = elut;
             op.in_off = off[n.inputs[0]];
         } else {
             err = "operator " + std::to_string(n.op) + " is not implemented (supported: RESHAPE, CONV_2D 1xk, ADD const, MAX_POOL_2D, FULLY_CONNECTED, SOFTMAX)";
@@ -532,6 +553,118 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
     nn.out_scale = tout.scale();
     nn.out_zp = tout.zero_point();
     hp.nn_smem_bytes = nn.arena_bytes + ((max_row + 15) & ~15);
+
+    // ---------- fused plan: conv -> add(const)+act -> maxpool, twice, then fully connected -> softmax ----------
+    {
+        NnFusedDev &fu = nn.fused;
+        std::memset(&fu, 0, sizeof(fu));
+        auto find_conv = [&](int idx) -> const ConvSrc * {
+            for (const ConvSrc &c : conv_src)
+                if (c.op_index == idx) return &c;
+            return nullptr;
+        };
+        auto find_lut = [&](int idx) -> const std::vector<uint8_t> * {
+            for (const auto &l : lut_src)
+                if (l.first == idx) return &l.second;
+            return nullptr;
+        };
+        bool ok = nn.n_ops == 8 && nn.ops[0].kind == kNnConv1d && nn.ops[1].kind == kNnAddLut && nn.ops[2].kind == kNnMaxPool &&
+                  nn.ops[3].kind == kNnConv1d && nn.ops[4].kind == kNnAddLut && nn.ops[5].kind == kNnMaxPool && nn.ops[6].kind == kNnConv1d &&
+                  nn.ops[7].kind == kNnSoftmax && !exp_lut_src.empty();
+        int arena = 0;
+        auto alloc = [&](int bytes) {
+            int o = arena;
+            arena += (bytes + 15) & ~15;
+            return o;
+        };
+        for (int s2 = 0; ok && s2 < 2; s2++) {
+            const NnOpDev &cv = nn.ops[3 * s2], &ad = nn.ops[3 * s2 + 1], &pl = nn.ops[3 * s2 + 2];
+            const ConvSrc *cs = find_conv(3 * s2);
+            const std::vector<uint8_t> *lut = find_lut(3 * s2 + 1);
+            NnFusedStage &st = fu.st[s2];
+            const int cp = (cv.in_c + 15) & ~15;
+            // the pool must run along the conv width (tensor reshaped to [1, W, 1, C]) with window == stride, no padding
+            ok = cs && lut && cv.stride_w == 1 && cv.kw == 7 && (cp == 16 || cp == 32) && cv.out_w == cv.in_w && ad.n_const == cv.out_c &&
+                 ad.n_elems == cv.out_w * cv.out_c && pl.in_w == 1 && pl.kw == 1 && pl.in_h == cv.out_w && pl.in_c == cv.out_c && pl.kh == 7 &&
+                 pl.stride_h == 7 && pl.pad_h == 0 && pl.out_h * 7 == pl.in_h && pl.out_w == 1;
+            if (s2 == 0) ok = ok && cv.in_w == kFrames && cv.in_c == kCepstra;
+            if (!ok) break;
+            st.in_w = cv.in_w;
+            st.in_c = cv.in_c;
+            st.cp = cp;
+            st.kw = cv.kw;
+            st.pad_w = cv.pad_w;
+            st.out_c = cv.out_c;
+            st.pool = pl.kh;
+            st.pool_out = pl.out_h;
+            st.in_zp = cv.in_zp;
+            st.conv_out_zp = cv.out_zp;
+            st.conv_act_min = cv.act_min;
+            st.conv_act_max = cv.act_max;
+            st.pool_act_min = pl.act_min;
+            st.pool_act_max = pl.act_max;
+            st.in_rows = cv.in_w + cv.kw - 1;
+            std::vector<int32_t> packed(static_cast<size_t>(cv.out_c) * cv.kw * (cp / 4), 0), bias(cv.out_c);
+            for (int oc = 0; oc < cv.out_c; oc++) {
+                int32_t wsum = 0;
+                for (int kx = 0; kx < cv.kw; kx++)
+                    for (int c2 = 0; c2 < cv.in_c; c2++) {
+                        const int8_t wv = cs->w[(oc * cv.kw + kx) * cv.in_c + c2];
+                        reinterpret_cast<uint8_t *>(packed.data())[(static_cast<size_t>(oc) * cv.kw + kx) * cp + c2] = static_cast<uint8_t>(wv);
+                        wsum += wv;
+                    }
+                bias[oc] = cs->raw_bias[oc] + (-cv.in_zp) * wsum;
+            }
+            b.bind(st.weights, b.push(packed.data(), packed.size() * 4));
+            b.bind(st.bias, b.push(bias.data(), bias.size() * 4));
+            b.bind(st.mult, b.push(cs->mult.data(), cs->mult.size() * 4));
+            b.bind(st.shift, b.push(cs->shift.data(), cs->shift.size() * 4));
+            b.bind(st.lut, b.push(lut->data(), lut->size()));
+        }
+        if (ok) {
+            const NnOpDev &fc = nn.ops[6], &sm = nn.ops[7];
+            const ConvSrc *cs = find_conv(6);
+            ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fu.st[1].out_c && fu.st[1].pool_out == 1 && fu.st[1].in_w == fu.st[0].pool_out &&
+                 fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
+            if (ok) {
+                NnFusedStage &s0 = fu.st[0], &s1 = fu.st[1];
+                s0.in_off = alloc(s0.in_rows * s0.cp);
+                s1.in_off = alloc(s1.in_rows * s1.cp);
+                fu.fc_in_off = alloc(fc.in_c);
+                fu.tail_off = alloc(64);
+                s0.out_off = s1.in_off;  // stage 0 writes stage 1's padded input
+                s0.out_cp = s1.cp;
+                s0.out_row0 = s1.pad_w;
+                s0.out_rows = s1.in_rows;
+                s0.out_fill = s1.in_zp;
+                s1.out_off = fu.fc_in_off;  // stage 1 writes the dense FC input
+                s1.out_cp = fc.in_c;
+                s1.out_row0 = 0;
+                s1.out_rows = 1;
+                s1.out_fill = 0;
+                fu.fc_d = fc.in_c;
+                fu.fc_o = fc.out_c;
+                fu.fc_in_zp = fc.in_zp;
+                fu.fc_out_zp = fc.out_zp;
+                fu.fc_act_min = fc.act_min;
+                fu.fc_act_max = fc.act_max;
+                fu.fc_mult = cs->mult[0];
+                fu.fc_shift = cs->shift[0];
+                std::vector<int32_t> fbias(fc.out_c);
+                for (int oc = 0; oc < fc.out_c; oc++) {
+                    int32_t wsum = 0;
+                    for (int d = 0; d < fc.in_c; d++) wsum += cs->w[oc * fc.in_c + d];
+                    fbias[oc] = cs->raw_bias[oc] + (-fc.in_zp) * wsum;
+                }
+                b.bind(fu.fc_w, b.push(cs->w, static_cast<size_t>(fc.out_c) * fc.in_c));
+                b.bind(fu.fc_bias, b.push(fbias.data(), fbias.size() * 4));
+                b.bind(fu.exp_lut, b.push(exp_lut_src.data(), exp_lut_src.size() * 4));
+                fu.enabled = 1;
+                if (arena > hp.nn_smem_bytes) hp.nn_smem_bytes = arena;
+            }
+        }
+        if (!ok) std::memset(&fu, 0, sizeof(fu));
+    }
     if (hp.nn_smem_bytes > nn_smem_capacity(false)) {
         err = "classifier activations do not fit the fused kernel's shared-memory overlay";
         return EIKWS_ERR_UNSUPPORTED;
