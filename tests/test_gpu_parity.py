@@ -12,7 +12,7 @@ from oracle_lib import PortOracle
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ("l476", "l432")
+MODELS = ("l476", "l432", "gsc12")
 FEATURE_TOL = 1e-5  # north-star tolerance on the float MFCC coefficients (we additionally assert exact equality)
 
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(eikws):
         assert hasattr(lib, n), f"{n} declared in eikws_b200.h but not exported"
 
 
-@pytest.mark.parametrize("name", ["l476", "l432"])
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12"])
 def test_host_plan_filterbank_matches_reference(eikws, name):
     fb, mult, shift = eikws.debug_host_plan(name)
     g = np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))

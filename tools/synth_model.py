@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Synthesise the 12-label (10 keywords + _noise/_unknown) int8 model of BASELINE.json config 4.
+
+The reference ships no such model, so one is derived from its L432 export (the copy whose generated files use
+include-path-relative includes) IN THE SAME GENERATED-FILE FORMAT, so that
+(1) the unmodified reference SDK can be compiled against it as the oracle, and (2) the product ingests it through the
+very same Register_*/trained_model_init boundary as a real Edge Impulse export.
+
+    python tools/synth_model.py <L432 export root> <out dir>
+
+Nothing from the reference is stored in this repo: its generated files are read as TEMPLATES at generation time and
+only the data tables are substituted (regex), the result is written under the (git-ignored) output directory:
+    <out>/model-parameters/{model_metadata.h,dsp_blocks.h}   <out>/tflite-model/trained_model_compiled.{h,cpp}
+New tables (seeded numpy PRNG, seed 0x12AB): every conv / fully-connected weight ~ clip(round(N(0,35))), per-channel
+weight scales = shipped scale x log-uniform[0.7,1.4], ADD constants uniform[-127,127], FC becomes [12,10] with
+bias ~ U[-400,400]; activation scales/zero points are kept so the graph stays numerically sane.
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+LABELS = ["_noise", "_unknown", "down", "go", "left", "no", "off", "on", "right", "stop", "up", "yes"]
+SEED = 0x12AB
+
+
+def fmt_int_array(a, per_line=16):
+    a = [int(v) for v in a]
+    lines = [", ".join(str(v) for v in a[i:i + per_line]) + ", " for i in range(0, len(a), per_line)]
+    return "{ \n  " + "\n  ".join(lines) + "\n}"
+
+
+def fmt_float_array(a):
+    return ", ".join(repr(float(np.float32(v).astype(np.float64))) if False else f"{float(v):.20g}" for v in a) + ", "
+
+
+def sub_one(pattern, repl, text, flags=re.S):
+    new, n = re.subn(pattern, lambda m: repl, text, count=1, flags=flags)
+    if n != 1:
+        raise RuntimeError("template pattern not found: " + pattern[:60])
+    return new
+
+
+def set_data(text, idx, ctype, dim_expr, values):
+    pat = r"const ALIGN\(8\) \w+ tensor_data%d\[[^\]]*\] = \{.*?\};" % idx
+    return sub_one(pat, f"const ALIGN(8) {ctype} tensor_data{idx}[{dim_expr}] = {fmt_int_array(values)};", text)
+
+
+def set_dims(text, idx, dims):
+    pat = r"const TfArray<\d+, int> tensor_dimension%d = \{[^;]*\};" % idx
+    return sub_one(pat, f"const TfArray<{len(dims)}, int> tensor_dimension{idx} = {{ {len(dims)}, {{ {','.join(str(d) for d in dims)} }} }};", text)
+
+
+def get_scales(text, idx):
+    m = re.search(r"const TfArray<(\d+), float> quant%d_scale = \{ \d+, \{ ([^}]*)\} \};" % idx, text)
+    return np.array([float(v) for v in m.group(2).split(",") if v.strip()], np.float64)
+
+
+def set_scales(text, idx, scales):
+    n = len(scales)
+    text = sub_one(r"const TfArray<\d+, float> quant%d_scale = \{[^;]*\};" % idx,
+                   f"const TfArray<{n}, float> quant{idx}_scale = {{ {n}, {{ {fmt_float_array(scales)}}} }};", text)
+    return sub_one(r"const TfArray<\d+, int> quant%d_zero = \{[^;]*\};" % idx,
+                   f"const TfArray<{n}, int> quant{idx}_zero = {{ {n}, {{ {','.join(['0'] * n)} }} }};", text)
+
+
+def set_tensor_bytes(text, data_name, nbytes):
+    # tensorData[] row of a constant tensor: { kTfLiteMmapRo, <type>, (void*)tensor_dataN, (TfLiteIntArray*)&tensor_dimensionN, <bytes>, ...
+    pat = r"(\(void\*\)%s, \(TfLiteIntArray\*\)&tensor_dimension\d+, )\d+(,)" % data_name
+    new, n = re.subn(pat, lambda m: m.group(1) + str(nbytes) + m.group(2), text, count=1)
+    if n != 1:
+        raise RuntimeError("tensorData row not found for " + data_name)
+    return new
+
+
+def set_arena_tensor_bytes(text, dim_idx, nbytes):
+    pat = r"(tensor_arena \+ \d+, \(TfLiteIntArray\*\)&tensor_dimension%d, )\d+(,)" % dim_idx
+    new, n = re.subn(pat, lambda m: m.group(1) + str(nbytes) + m.group(2), text, count=1)
+    if n != 1:
+        raise RuntimeError("arena tensor row not found for dimension %d" % dim_idx)
+    return new
+
+
+def main(src_root, out_root):
+    rng = np.random.default_rng(SEED)
+    n = len(LABELS)
+    cpp = open(os.path.join(src_root, "tflite-model", "trained_model_compiled.cpp")).read()
+    hdr = open(os.path.join(src_root, "tflite-model", "trained_model_compiled.h")).read()
+    meta = open(os.path.join(src_root, "model-parameters", "model_metadata.h")).read()
+    blocks = open(os.path.join(src_root, "model-parameters", "dsp_blocks.h")).read()
+
+    def weights(count):
+        return np.clip(np.round(rng.normal(0, 35, count)), -127, 127).astype(np.int64)
+
+    # conv1 (tensor 7, per-channel scales 7, bias-scales 6), conv2 (9 / 8), ADD constants 2 and 3
+    cpp = set_data(cpp, 7, "int8_t", "30*1*7*13", weights(30 * 7 * 13))
+    cpp = set_data(cpp, 9, "int8_t", "10*1*7*30", weights(10 * 7 * 30))
+    cpp = set_data(cpp, 2, "int8_t", "30", rng.integers(-127, 128, 30))
+    cpp = set_data(cpp, 3, "int8_t", "10", rng.integers(-127, 128, 10))
+    in_scale = {7: get_scales(cpp, 16)[0], 9: get_scales(cpp, 22)[0]}
+    for w_idx, b_idx in ((7, 6), (9, 8)):
+        s = get_scales(cpp, w_idx) * np.exp(rng.uniform(np.log(0.7), np.log(1.4), len(get_scales(cpp, w_idx))))
+        s = s.astype(np.float32).astype(np.float64)
+        cpp = set_scales(cpp, w_idx, s)
+        cpp = set_scales(cpp, b_idx, (s * in_scale[w_idx]).astype(np.float32).astype(np.float64))
+    # fully connected: weights [12,10] (tensor 5), bias int32[12] (tensor 4), outputs 29/30 become [1,12]
+    cpp = set_data(cpp, 5, "int8_t", f"{n}*10", weights(n * 10))
+    cpp = set_dims(cpp, 5, [n, 10])
+    cpp = set_data(cpp, 4, "int32_t", str(n), rng.integers(-400, 401, n))
+    cpp = set_dims(cpp, 4, [n])
+    cpp = set_dims(cpp, 29, [1, n])
+    cpp = set_dims(cpp, 30, [1, n])
+    cpp = set_tensor_bytes(cpp, "tensor_data4", 4 * n)
+    cpp = set_tensor_bytes(cpp, "tensor_data5", 10 * n)
+    cpp = set_arena_tensor_bytes(cpp, 29, n)
+    cpp = set_arena_tensor_bytes(cpp, 30, n)
+    meta = sub_one(r"#define EI_CLASSIFIER_LABEL_COUNT\s+\d+", f"#define EI_CLASSIFIER_LABEL_COUNT                {n}", meta)
+    meta = sub_one(r"const char\* ei_classifier_inferencing_categories\[\] = \{[^}]*\};",
+                   "const char* ei_classifier_inferencing_categories[] = { " + ", ".join(f'"{l}"' for l in LABELS) + " };", meta)
+    for sub, name, text in (("tflite-model", "trained_model_compiled.cpp", cpp), ("tflite-model", "trained_model_compiled.h", hdr),
+                            ("model-parameters", "model_metadata.h", meta), ("model-parameters", "dsp_blocks.h", blocks)):
+        os.makedirs(os.path.join(out_root, sub), exist_ok=True)
+        with open(os.path.join(out_root, sub, name), "w") as f:
+            f.write(text)
+    print("synthesised", n, "label model under", out_root)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) != 3:
+        sys.exit(__doc__)
+    main(sys.argv[1], sys.argv[2])
