@@ -51,6 +51,7 @@ def load_library() -> C.CDLL:
     L.eikws_launch_count.restype = u64
     L.eikws_launch_count.argtypes = [vp]
     L.eikws_set_ctas_per_sm.argtypes = [vp, i32]
+    L.eikws_set_skew_ns.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -116,6 +117,9 @@ class Impulse:
 
     def set_ctas_per_sm(self, n: int):
         _check(self._lib.eikws_set_ctas_per_sm(self._h, n))
+
+    def set_skew_ns(self, ns: int):
+        _check(self._lib.eikws_set_skew_ns(self._h, ns))
 
     # ---- host (numpy) batch API: H2D + kernel + D2H inside the call -----------------------------------
     def run_classifier(self, clips: np.ndarray) -> np.ndarray:

@@ -27,7 +27,8 @@ struct eikws_handle {
     HostPlan host;
     DevicePlan dev;
     int sm_count = 148;
-    int ctas_per_sm = 3;
+    int ctas_per_sm = 4;
+    int skew_ns = 14000;  // start offset between the CTAs that share an SM (see kernels.cu)
     uint64_t launches = 0;
     std::mutex mu;  // serialises the host-buffer and single-clip paths (they share staging buffers)
     // staging for the host-buffer entry points
@@ -95,11 +96,14 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.features_in = features_in;
     a.n_clips = n;
     a.run_nn = run_nn;
+    a.nn_fused = h->host.dev.nn.fused.enabled != 0;
     a.probs = probs;
     a.features_out = feat;
     a.qfeatures_out = qfeat;
     a.debug_taps = dbg;
     a.grid = grid_for(h, n);
+    a.sm_count = h->sm_count;
+    a.skew_ns = (n >= static_cast<size_t>(h->sm_count) * h->ctas_per_sm * 8) ? h->skew_ns : 0;  // only worth it for long launches
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
     a.stream = st;
     cudaError_t e = launch_run_classifier(a);
@@ -214,6 +218,11 @@ uint64_t eikws_launch_count(const eikws_handle *h) { return h ? h->launches : 0;
 int eikws_set_ctas_per_sm(eikws_handle *h, int n) {  // tuning knob (not in the public header)
     if (!h || n < 1 || n > 8) return EIKWS_ERR_BAD_ARG;
     h->ctas_per_sm = n;
+    return EIKWS_OK;
+}
+int eikws_set_skew_ns(eikws_handle *h, int ns) {  // tuning knob (not in the public header)
+    if (!h || ns < 0 || ns > 1000000) return EIKWS_ERR_BAD_ARG;
+    h->skew_ns = ns;
     return EIKWS_OK;
 }
 

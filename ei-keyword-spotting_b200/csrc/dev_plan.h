@@ -90,6 +90,7 @@ struct NnFusedDev {
     NnFusedStage st[2];
     // tail: FULLY_CONNECTED [fc_d] -> [fc_o], SOFTMAX over fc_o
     int32_t fc_in_off, fc_d, fc_o, fc_in_zp, fc_out_zp, fc_act_min, fc_act_max, fc_mult, fc_shift;
+    int32_t tail_pool, tail_pool_act_min, tail_pool_act_max;  // stage 1 leaves its max-pool (over tail_pool positions) to the tail
     int32_t tail_off;        // scratch for the fc output / softmax output bytes
     const int8_t *fc_w;      // [fc_o][fc_d]
     const int32_t *fc_bias;  // [fc_o] bias + in_offset * sum(weights)

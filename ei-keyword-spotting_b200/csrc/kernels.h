@@ -16,11 +16,14 @@ struct LaunchArgs {
     const float *features_in = nullptr;  // device: run_inference only (clips ignored)
     size_t n_clips = 0;
     bool run_nn = true;
+    bool nn_fused = false;               // the plan has a fused classifier (NnFusedDev.enabled)
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
     float *debug_taps = nullptr;         // device, tests only: [n_clips][debug_tap_floats()] (int16 classify path)
     int grid = 0;
+    int sm_count = 0;                    // SMs of the device (CTA j of an SM = blockIdx / sm_count)
+    int skew_ns = 0;                     // start offset between co-resident CTAs (0 = none)
     int nn_smem_bytes = 0;               // activation arena + conv row scratch
     cudaStream_t stream = nullptr;
 };

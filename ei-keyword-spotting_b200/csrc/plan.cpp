@@ -584,7 +584,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             NnFusedStage &st = fu.st[s2];
             const int cp = (cv.in_c + 15) & ~15;
             // the pool must run along the conv width (tensor reshaped to [1, W, 1, C]) with window == stride, no padding
-            ok = cs && lut && cv.stride_w == 1 && cv.kw == 7 && (cp == 16 || cp == 32) && cv.out_w == cv.in_w && ad.n_const == cv.out_c &&
+            ok = cs && lut && cv.stride_w == 1 && cv.kw == 7 && cp == (s2 == 0 ? 16 : 32) && cv.out_w == cv.in_w && ad.n_const == cv.out_c &&
                  ad.n_elems == cv.out_w * cv.out_c && pl.in_w == 1 && pl.kw == 1 && pl.in_h == cv.out_w && pl.in_c == cv.out_c && pl.kh == 7 &&
                  pl.stride_h == 7 && pl.pad_h == 0 && pl.out_h * 7 == pl.in_h && pl.out_w == 1;
             if (s2 == 0) ok = ok && cv.in_w == kFrames && cv.in_c == kCepstra;
@@ -597,12 +597,21 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             st.out_c = cv.out_c;
             st.pool = pl.kh;
             st.pool_out = pl.out_h;
+            if (s2 == 1) {
+                // the second block is tiny (7 x 10 outputs): one thread per conv output, the max-pool moves to the tail warp
+                ok = pl.out_h == 1;
+                st.pool = 1;
+                st.pool_out = cv.out_w;
+                fu.tail_pool = pl.kh;
+                fu.tail_pool_act_min = pl.act_min;
+                fu.tail_pool_act_max = pl.act_max;
+            }
             st.in_zp = cv.in_zp;
             st.conv_out_zp = cv.out_zp;
             st.conv_act_min = cv.act_min;
             st.conv_act_max = cv.act_max;
-            st.pool_act_min = pl.act_min;
-            st.pool_act_max = pl.act_max;
+            st.pool_act_min = s2 == 1 ? -128 : pl.act_min;
+            st.pool_act_max = s2 == 1 ? 127 : pl.act_max;
             st.in_rows = cv.in_w + cv.kw - 1;
             std::vector<int32_t> packed(static_cast<size_t>(cv.out_c) * cv.kw * (cp / 4), 0), bias(cv.out_c);
             for (int oc = 0; oc < cv.out_c; oc++) {
@@ -624,13 +633,13 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
         if (ok) {
             const NnOpDev &fc = nn.ops[6], &sm = nn.ops[7];
             const ConvSrc *cs = find_conv(6);
-            ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fu.st[1].out_c && fu.st[1].pool_out == 1 && fu.st[1].in_w == fu.st[0].pool_out &&
+            ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fu.st[1].out_c && fu.st[1].pool_out == fu.tail_pool && fu.st[1].in_w == fu.st[0].pool_out &&
                  fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
             if (ok) {
                 NnFusedStage &s0 = fu.st[0], &s1 = fu.st[1];
                 s0.in_off = alloc(s0.in_rows * s0.cp);
                 s1.in_off = alloc(s1.in_rows * s1.cp);
-                fu.fc_in_off = alloc(fc.in_c);
+                fu.fc_in_off = alloc(fc.in_c * fu.tail_pool);  // [tail_pool positions][fc_d] conv+add outputs of block 2
                 fu.tail_off = alloc(64);
                 s0.out_off = s1.in_off;  // stage 0 writes stage 1's padded input
                 s0.out_cp = s1.cp;
@@ -640,7 +649,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 s1.out_off = fu.fc_in_off;  // stage 1 writes the dense FC input
                 s1.out_cp = fc.in_c;
                 s1.out_row0 = 0;
-                s1.out_rows = 1;
+                s1.out_rows = fu.tail_pool;
                 s1.out_fill = 0;
                 fu.fc_d = fc.in_c;
                 fu.fc_o = fc.out_c;
