@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-clips-per-core", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default=MODEL, help="l476 (default, BASELINE configs[1]), gsc12 (config 4), l476f32 (config 5)")
+    ap.add_argument("--f32-input", action="store_true", help="feed float32 samples (64,000 B/clip) instead of int16 PCM (config 5)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +154,9 @@ def main():
     n_gpus = world
     config = {"workload": f"BASELINE configs[1]: batch {args.clips_per_gpu} synthetic 1-s 16 kHz int16 clips per GPU, "
                           f"L476 4-label int8 model (MFCC+CMVN+int8 CNN fused), inputs ({args.clips_per_gpu * 32000 / 1e9:.2f} GB/GPU) larger than L2",
-              "model": "l476_yes_no (EON-compiled int8, 4 labels)", "clips_per_gpu": args.clips_per_gpu,
+              "model": {"l476": "l476_yes_no (EON-compiled int8, 4 labels)", "gsc12": "synthesised 12-label int8 model (BASELINE config 4)",
+                        "l476f32": "float32 twin of l476 (BASELINE config 5)", "l432": "l432 (int8, 3 labels)"}[args.model],
+              "input": "float32 samples" if args.f32_input else "int16 PCM", "clips_per_gpu": args.clips_per_gpu,
               "sharding": f"{n_gpus} independent shard(s), no collective on the data path"}
 
     # ------------------------------------------------------------------ reference arm
@@ -192,9 +196,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    imp = eikws.Impulse(MODEL, device=local_rank)
+    imp = eikws.Impulse(args.model, device=local_rank)
     n = args.clips_per_gpu
     clips = imp.synth_clips_device(n, first_clip=rank * n)
+    if args.f32_input:  # the float the demo callback would deliver: x / 32768 (exact)
+        clips = (clips.to(torch.float32) / 32768.0).contiguous()
+    algo_bytes = N_SAMPLES * (4 if args.f32_input else 2) + 4 * imp.label_count
     probs = torch.empty((n, imp.label_count), dtype=torch.float32, device=dev)
     torch.cuda.synchronize()
 
@@ -227,7 +234,7 @@ def main():
     value = n_gpus * n * args.steps / (elapsed_ms * 1e-3)
 
     # ------------------------------------------------------------------ end to end through the host-buffer C ABI
-    h_clips = torch.empty((n, N_SAMPLES), dtype=torch.int16, pin_memory=True)
+    h_clips = torch.empty((n, N_SAMPLES), dtype=clips.dtype, pin_memory=True)
     h_clips.copy_(clips)
     h_probs = torch.empty((n, imp.label_count), dtype=torch.float32, pin_memory=True)
     torch.cuda.synchronize()
@@ -235,7 +242,8 @@ def main():
     lib = eikws.load_library()
 
     def e2e_step():
-        rc = lib.eikws_classify_i16_host(imp._h, C.c_void_p(h_clips.data_ptr()), n, C.c_void_p(h_probs.data_ptr()))
+        fn = lib.eikws_classify_f32_host if args.f32_input else lib.eikws_classify_i16_host
+        rc = fn(imp._h, C.c_void_p(h_clips.data_ptr()), n, C.c_void_p(h_probs.data_ptr()))
         assert rc == 0, lib.eikws_last_error()
 
     e2e_step()
@@ -254,17 +262,17 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         kernel_ms = elapsed_ms / max(launches, 1)
-        achieved = n * ALGO_BYTES_PER_CLIP / (kernel_ms * 1e-3) / 1e9
+        achieved = n * algo_bytes / (kernel_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32+f64 MFCC (bit-exact to the reference), int8 CNN", "data": "synthetic", "config": config,
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * N_SAMPLES * 2, "d2h_bytes_per_step": n * imp.label_count * 4,
-                        "steps": args.e2e_steps, "api": "eikws_classify_i16_host (pinned host buffers)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * N_SAMPLES * clips.element_size(), "d2h_bytes_per_step": n * imp.label_count * 4,
+                        "steps": args.e2e_steps, "api": ("eikws_classify_f32_host" if args.f32_input else "eikws_classify_i16_host") + " (pinned host buffers, 8192-clip chunks on two streams)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": peak_src, "kernel": "eikws_run_classifier_kernel<int16,mfcc,nn>",
-                             "algo_bytes_per_clip": ALGO_BYTES_PER_CLIP, "kernel_ms": kernel_ms}}
+                             "algo_bytes_per_clip": algo_bytes, "kernel_ms": kernel_ms}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

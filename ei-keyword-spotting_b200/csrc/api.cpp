@@ -41,7 +41,8 @@ struct eikws_handle {
     int8_t *d_qfeat = nullptr;
     size_t d_qfeat_bytes = 0;
     float *h_pinned = nullptr;  // one clip of floats for eikws_run_classifier_signal
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    size_t host_chunk_clips = 8192;  // host-buffer path: clips per pipelined chunk (262 MB of int16 PCM)
 };
 
 namespace {
@@ -97,6 +98,8 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.n_clips = n;
     a.run_nn = run_nn;
     a.nn_fused = h->host.dev.nn.fused.enabled != 0;
+    a.nn_float = h->host.dev.nn.float_mode != 0;
+    if (a.nn_float && qfeat) return fail(EIKWS_ERR_BAD_ARG, "a float32 model has no quantised input tensor");
     a.probs = probs;
     a.features_out = feat;
     a.qfeatures_out = qfeat;
@@ -196,6 +199,7 @@ void eikws_destroy(eikws_handle *h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_probs) cudaFree(h->d_probs);
     if (h->d_feat) cudaFree(h->d_feat);
@@ -269,6 +273,8 @@ int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n, uint64_t f
 }
 
 // ---- host-buffer entry points (synchronous) ---------------------------------------------------------------
+// Host-buffer path: the batch is cut into chunks that alternate between two streams, so the H2D copy of chunk i+1
+// (PCIe) overlaps the kernel and the D2H of chunk i.  The staging buffers hold the whole batch; results land in place.
 static int host_run(eikws_handle *h, const void *in, size_t in_bytes_per_clip, bool f32, const float *features_in, size_t n, bool run_nn,
                     float *probs, float *features, int8_t *qfeatures) {
     if (n == 0) return EIKWS_OK;
@@ -277,30 +283,44 @@ static int host_run(eikws_handle *h, const void *in, size_t in_bytes_per_clip, b
     const size_t L = h->graph.labels.size(), F = h->graph.nn_input_frame_size;
     int rc;
     cudaError_t e;
-    const void *d_src = nullptr;
+    if (!h->stream2 && (e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
     if (features_in) {
         if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
-        if ((e = cudaMemcpyAsync(h->d_feat, features_in, n * F * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
-            return cuda_fail(e, "H2D features");
     } else {
         if ((rc = ensure(&h->d_in, &h->d_in_bytes, n * in_bytes_per_clip))) return rc;
-        if ((e = cudaMemcpyAsync(h->d_in, in, n * in_bytes_per_clip, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess)
-            return cuda_fail(e, "H2D clips");
-        d_src = h->d_in;
         if (features && (rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
     }
     if (probs && (rc = ensure(reinterpret_cast<void **>(&h->d_probs), &h->d_probs_bytes, n * L * 4))) return rc;
     if (qfeatures && (rc = ensure(reinterpret_cast<void **>(&h->d_qfeat), &h->d_qfeat_bytes, n * F))) return rc;
-    rc = launch(h, d_src, f32, features_in ? h->d_feat : nullptr, n, run_nn, probs ? h->d_probs : nullptr,
-                (features && !features_in) ? h->d_feat : nullptr, qfeatures ? h->d_qfeat : nullptr, h->stream);
-    if (rc) return rc;
-    if (probs && (e = cudaMemcpyAsync(probs, h->d_probs, n * L * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
-        return cuda_fail(e, "D2H probs");
-    if (features && !features_in && (e = cudaMemcpyAsync(features, h->d_feat, n * F * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
-        return cuda_fail(e, "D2H features");
-    if (qfeatures && (e = cudaMemcpyAsync(qfeatures, h->d_qfeat, n * F, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
-        return cuda_fail(e, "D2H qfeatures");
+    const size_t chunk = h->host_chunk_clips;
+    int ci = 0;
+    for (size_t off = 0; off < n; off += chunk, ci++) {
+        const size_t m = n - off < chunk ? n - off : chunk;
+        cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
+        const void *d_src = nullptr;
+        if (features_in) {
+            if ((e = cudaMemcpyAsync(h->d_feat + off * F, features_in + off * F, m * F * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                return cuda_fail(e, "H2D features");
+        } else {
+            uint8_t *dst = static_cast<uint8_t *>(h->d_in) + off * in_bytes_per_clip;
+            if ((e = cudaMemcpyAsync(dst, static_cast<const uint8_t *>(in) + off * in_bytes_per_clip, m * in_bytes_per_clip, cudaMemcpyHostToDevice,
+                                     st)) != cudaSuccess)
+                return cuda_fail(e, "H2D clips");
+            d_src = dst;
+        }
+        rc = launch(h, d_src, f32, features_in ? h->d_feat + off * F : nullptr, m, run_nn, probs ? h->d_probs + off * L : nullptr,
+                    (features && !features_in) ? h->d_feat + off * F : nullptr, qfeatures ? h->d_qfeat + off * F : nullptr, st);
+        if (rc) return rc;
+        if (probs && (e = cudaMemcpyAsync(probs + off * L, h->d_probs + off * L, m * L * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return cuda_fail(e, "D2H probs");
+        if (features && !features_in &&
+            (e = cudaMemcpyAsync(features + off * F, h->d_feat + off * F, m * F * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return cuda_fail(e, "D2H features");
+        if (qfeatures && (e = cudaMemcpyAsync(qfeatures + off * F, h->d_qfeat + off * F, m * F, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            return cuda_fail(e, "D2H qfeatures");
+    }
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
+    if ((e = cudaStreamSynchronize(h->stream2)) != cudaSuccess) return cuda_fail(e, "kernel execution");
     return EIKWS_OK;
 }
 

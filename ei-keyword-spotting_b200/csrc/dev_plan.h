@@ -43,7 +43,10 @@ struct MfccDev {
 };
 
 // ---- classifier ------------------------------------------------------------------------------------
-enum NnOpKind : int32_t { kNnConv1d = 1, kNnAddLut = 2, kNnMaxPool = 3, kNnSoftmax = 4 };
+enum NnOpKind : int32_t {
+    kNnConv1d = 1, kNnAddLut = 2, kNnMaxPool = 3, kNnSoftmax = 4,           // int8 graph
+    kNnConv1dF32 = 11, kNnAddF32 = 12, kNnMaxPoolF32 = 13, kNnSoftmaxF32 = 14  // float32 twin (BASELINE config 5)
+};
 
 struct NnOpDev {
     int32_t kind;
@@ -63,6 +66,10 @@ struct NnOpDev {
     const int32_t *shift;     // conv: [out_c] shift (positive = left)
     const uint8_t *lut;       // add: [n_const][256] output byte for input byte q (index q+128)
     const int32_t *exp_lut;   // softmax: [256] exp_on_negative_values for diff = -i, or -1 if below diff_min
+    // float32 ops
+    const float *wf;          // conv/fc: [kw*in_c][out_c] (transposed so that lanes over out_c read consecutively)
+    const float *bf;          // conv/fc: [out_c] bias or null; add: [n_const] constant operand
+    float fmin, fmax;         // fused activation range; softmax: fmin = beta
 };
 
 constexpr int kMaxNnOps = 16;
@@ -107,6 +114,7 @@ struct NnDev {
     int32_t row_bytes;    // scratch for the zero-point padded conv input row
     float out_scale;
     int32_t out_zp;
+    int32_t float_mode;   // 1: every activation tensor is float32 (offsets are still bytes)
     NnOpDev ops[kMaxNnOps];
     NnFusedDev fused;
 };

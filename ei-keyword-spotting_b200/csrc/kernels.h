@@ -17,6 +17,7 @@ struct LaunchArgs {
     size_t n_clips = 0;
     bool run_nn = true;
     bool nn_fused = false;               // the plan has a fused classifier (NnFusedDev.enabled)
+    bool nn_float = false;               // float32 graph (NnDev.float_mode)
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
@@ -34,5 +35,7 @@ int kernel_threads();
 int debug_tap_floats();  // P[129][49] + logmel[49][33] + cepstra[49][13]
 // bytes of shared memory available to the classifier arena inside the fused kernel's overlay
 int nn_smem_capacity(bool input_is_f32);
+// float32 graphs may also use the (dead after CMVN) GT area: up to the mbarrier
+int nn_smem_capacity_float_graph();
 
 }  // namespace eikws

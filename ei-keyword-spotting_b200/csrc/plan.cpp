@@ -179,6 +179,185 @@ int same_or_valid_pad(int padding, int stride, int dilation, int in, int filt) {
     return total / 2;
 }
 
+
+// ---- float32 graph (BASELINE config 5): same operator set, TFLite float reference semantics ----------------------
+// CalculateActivationRange (kernel_util.h): None [lowest,max], Relu [0,max], Relu6 [0,6], ReluN1To1 [-1,1]
+void activation_range_f32(int act, float *lo, float *hi) {
+    *lo = -FLT_MAX;
+    *hi = FLT_MAX;
+    if (act == 1) *lo = 0.0f;
+    else if (act == 3) { *lo = 0.0f; *hi = 6.0f; }
+    else if (act == 2) { *lo = -1.0f; *hi = 1.0f; }
+}
+
+int build_float_nn(const ModelGraph &g, HostPlan &hp, Builder &b, std::string &err) {
+    NnDev &nn = hp.dev.nn;
+    MfccDev &mf = hp.dev.mfcc;
+    const TensorDesc &tin = g.tensors[g.input], &tout = g.tensors[g.output];
+    if (tin.bytes != kFeatures * 4 || static_cast<size_t>(tout.bytes) != g.labels.size() * 4) {
+        err = "input/output tensor size does not match feature/label count";
+        return EIKWS_ERR_SHAPES_DONT_MATCH;
+    }
+    mf.q_scale = 1.0f;
+    mf.q_zp = 0;
+    mf.input_is_int8 = 0;
+    uint32_t max_bytes = 0;
+    for (const TensorDesc &t : g.tensors)
+        if (!t.is_const && t.bytes > max_bytes) max_bytes = t.bytes;
+    const int buf_bytes = static_cast<int>((max_bytes + 15) & ~15u);
+    std::vector<int> off(g.tensors.size(), -1);
+    off[g.input] = 0;
+    nn.n_ops = 0;
+    nn.float_mode = 1;
+    auto other = [&](int o) { return o == 0 ? buf_bytes : 0; };
+    for (const NodeDesc &n : g.nodes) {
+        if (n.op == kOpReshape) {
+            if (n.inputs.empty() || off[n.inputs[0]] < 0) {
+                err = "reshape of an unplaced tensor";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
+            off[n.outputs[0]] = off[n.inputs[0]];
+            continue;
+        }
+        if (nn.n_ops >= kMaxNnOps) {
+            err = "graph has more compute nodes than kMaxNnOps";
+            return EIKWS_ERR_UNSUPPORTED;
+        }
+        NnOpDev &op = nn.ops[nn.n_ops];
+        std::memset(&op, 0, sizeof(op));
+        const TensorDesc &out = g.tensors[n.outputs[0]];
+        if (out.type != kF32) {
+            err = "mixed-type graph";
+            return EIKWS_ERR_UNSUPPORTED;
+        }
+        if (n.op == kOpConv2D || n.op == kOpFullyConnected) {
+            const TensorDesc &in = g.tensors[n.inputs[0]], &flt = g.tensors[n.inputs[1]];
+            const bool has_bias = n.inputs.size() > 2 && n.inputs[2] >= 0;
+            if (off[n.inputs[0]] < 0 || !flt.is_const || flt.type != kF32 || in.type != kF32 ||
+                (has_bias && (!g.tensors[n.inputs[2]].is_const || g.tensors[n.inputs[2]].type != kF32))) {
+                err = "conv/fc: unsupported operand types";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
+            op.kind = kNnConv1dF32;
+            if (n.op == kOpConv2D) {
+                int di[4], df[4], dq[4];
+                dims4(in, di);
+                dims4(flt, df);
+                dims4(out, dq);
+                if (di[0] != 1 || di[1] != 1 || df[1] != 1 || dq[1] != 1 || n.params[4] != 1 || df[3] != di[3] || dq[3] != df[0]) {
+                    err = "conv: only 1xk convolutions over [1,1,W,C] inputs with dilation 1 are implemented";
+                    return EIKWS_ERR_UNSUPPORTED;
+                }
+                op.in_w = di[2];
+                op.in_c = di[3];
+                op.out_w = dq[2];
+                op.out_c = dq[3];
+                op.kw = df[2];
+                op.stride_w = n.params[1];
+                op.pad_w = same_or_valid_pad(n.params[0], n.params[1], 1, di[2], df[2]);
+                activation_range_f32(n.params[3], &op.fmin, &op.fmax);
+            } else {
+                const int depth = flt.dims.back(), outc = out.dims.back();
+                if (static_cast<int>(in.bytes) != depth * 4 || static_cast<int>(flt.bytes) != depth * outc * 4 || static_cast<int>(out.bytes) != outc * 4) {
+                    err = "fully_connected: only batch 1 with a dense [out,in] filter is implemented";
+                    return EIKWS_ERR_UNSUPPORTED;
+                }
+                op.in_w = 1;
+                op.in_c = depth;
+                op.out_w = 1;
+                op.out_c = outc;
+                op.kw = 1;
+                op.stride_w = 1;
+                activation_range_f32(n.params[0], &op.fmin, &op.fmax);
+            }
+            const int K = op.kw * op.in_c;
+            const float *w = reinterpret_cast<const float *>(flt.data.data());
+            std::vector<float> wt(static_cast<size_t>(K) * op.out_c);
+            for (int oc = 0; oc < op.out_c; oc++)
+                for (int k = 0; k < K; k++) wt[static_cast<size_t>(k) * op.out_c + oc] = w[oc * K + k];
+            b.bind(op.wf, b.push(wt.data(), wt.size() * 4));
+            if (has_bias) b.bind(op.bf, b.push(g.tensors[n.inputs[2]].data.data(), g.tensors[n.inputs[2]].data.size()));
+            op.in_off = off[n.inputs[0]];
+        } else if (n.op == kOpAdd) {
+            int ia = n.inputs[0], ic = n.inputs[1];
+            if (g.tensors[ia].is_const && !g.tensors[ic].is_const) std::swap(ia, ic);  // float addition commutes exactly
+            const TensorDesc &a = g.tensors[ia], &cst = g.tensors[ic];
+            const size_t nc = cst.dims.size(), na = a.dims.size();
+            bool ok = !a.is_const && cst.is_const && off[ia] >= 0 && a.type == kF32 && cst.type == kF32 && nc <= na && out.bytes == a.bytes;
+            for (size_t i = 0; ok && i < nc; i++) ok = cst.dims[nc - 1 - i] == a.dims[na - 1 - i];
+            if (!ok || cst.bytes == 0 || a.bytes % cst.bytes) {
+                err = "add: only activation + trailing-dims constant is implemented";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
+            op.kind = kNnAddF32;
+            op.n_elems = static_cast<int32_t>(out.bytes / 4);
+            op.n_const = static_cast<int32_t>(cst.bytes / 4);
+            activation_range_f32(n.params[0], &op.fmin, &op.fmax);
+            b.bind(op.bf, b.push(cst.data.data(), cst.data.size()));
+            op.in_off = off[ia];
+        } else if (n.op == kOpMaxPool2D) {
+            const TensorDesc &in = g.tensors[n.inputs[0]];
+            int di[4], dq[4];
+            dims4(in, di);
+            dims4(out, dq);
+            if (off[n.inputs[0]] < 0 || in.type != kF32 || di[0] != 1 || di[3] != dq[3]) {
+                err = "max_pool: unsupported operand";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
+            op.kind = kNnMaxPoolF32;
+            op.in_h = di[1];
+            op.in_w = di[2];
+            op.in_c = di[3];
+            op.out_h = dq[1];
+            op.out_w = dq[2];
+            op.out_c = dq[3];
+            op.stride_w = n.params[1];
+            op.stride_h = n.params[2];
+            op.kw = n.params[3];
+            op.kh = n.params[4];
+            op.pad_h = same_or_valid_pad(n.params[0], op.stride_h, 1, op.in_h, op.kh);
+            op.pad_w = same_or_valid_pad(n.params[0], op.stride_w, 1, op.in_w, op.kw);
+            activation_range_f32(n.params[5], &op.fmin, &op.fmax);
+            op.in_off = off[n.inputs[0]];
+        } else if (n.op == kOpSoftmax) {
+            const TensorDesc &in = g.tensors[n.inputs[0]];
+            int outer = 1;
+            for (size_t i = 0; i + 1 < in.dims.size(); i++) outer *= in.dims[i];
+            if (off[n.inputs[0]] < 0 || in.type != kF32 || outer != 1) {
+                err = "softmax: only a single float row is implemented";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
+            op.kind = kNnSoftmaxF32;
+            op.n_elems = in.dims.back();
+            std::memcpy(&op.fmin, &n.params[0], 4);  // beta
+            op.in_off = off[n.inputs[0]];
+        } else {
+            err = "operator " + std::to_string(n.op) + " is not implemented for float32 graphs";
+            return EIKWS_ERR_UNSUPPORTED;
+        }
+        op.out_off = other(op.in_off);
+        off[n.outputs[0]] = op.out_off;
+        nn.n_ops++;
+    }
+    if (off[g.output] < 0) {
+        err = "output tensor is never produced";
+        return EIKWS_ERR_UNSUPPORTED;
+    }
+    nn.in_off = 0;
+    nn.out_off = off[g.output];
+    nn.n_in = kFeatures;
+    nn.n_out = static_cast<int32_t>(g.labels.size());
+    nn.arena_bytes = 2 * buf_bytes;
+    nn.out_scale = 1.0f;
+    nn.out_zp = 0;
+    hp.nn_smem_bytes = nn.arena_bytes;
+    if (hp.nn_smem_bytes > nn_smem_capacity_float_graph()) {
+        err = "float activations do not fit the fused kernel's shared-memory overlay";
+        return EIKWS_ERR_UNSUPPORTED;
+    }
+    return EIKWS_OK;
+}
+
 }  // namespace
 
 // QuantizeMultiplier (quantization_util.cc:53-91)
@@ -272,8 +451,14 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
     // ---------- classifier ----------
     NnDev &nn = hp.dev.nn;
     const TensorDesc &tin = g.tensors[g.input], &tout = g.tensors[g.output];
+    if (tin.type == kF32 && tout.type == kF32) {
+        int rc = build_float_nn(g, hp, b, err);
+        if (rc != EIKWS_OK) return rc;
+        for (const Fixup &f : b.fixups) hp.fixups.emplace_back(f.field_off, f.blob_off);
+        return EIKWS_OK;
+    }
     if (tin.type != kI8 || tout.type != kI8) {
-        err = "only int8-quantised models are supported by this build (input/output tensor type)";
+        err = "unsupported input/output tensor type (int8 and float32 graphs are implemented)";
         return EIKWS_ERR_UNSUPPORTED;
     }
     if (tin.bytes != kFeatures || static_cast<size_t>(tout.bytes) != g.labels.size()) {

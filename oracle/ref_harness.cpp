@@ -61,7 +61,7 @@ static int get_data_f32(size_t offset, size_t length, float *out) {
 
 // ---- tensor dump taken just before the arena is freed ------------------------
 #define REF_MAX_TENSORS 64
-#define REF_MAX_TENSOR_BYTES 4096
+#define REF_MAX_TENSOR_BYTES 8192
 static int g_dump_enabled = 0;
 static int g_dump_count = 0;
 static int g_dump_bytes[REF_MAX_TENSORS];

@@ -45,7 +45,7 @@ def crafted_features(n_labels_seed: int) -> np.ndarray:
 
 
 def main():
-    for mi, name in enumerate(("l476", "l432", "gsc12")):
+    for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32")):
         ref = RefOracle(name)
         specials = synth.special_clips()
         clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values()))])

@@ -32,6 +32,11 @@ def test_host_plan_filterbank_matches_reference(eikws, name):
     assert np.all((mult >= (1 << 30)) & (mult < (1 << 31))) and np.all(shift <= 0)
 
 
+def test_float_graph_is_lowered(eikws):
+    fb, mult, _ = eikws.debug_host_plan("l476f32")  # BASELINE config 5: float32 twin, no requantisation tables
+    assert fb.shape == (129, 32) and len(mult) == 0
+
+
 def test_malformed_model_is_rejected(eikws):
     lib = eikws.load_library()
     n = C.c_int(0)

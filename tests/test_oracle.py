@@ -8,7 +8,7 @@ import pytest
 from oracle_lib import PortOracle, RefOracle, have_ref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ("l476", "l432", "gsc12")
+MODELS = ("l476", "l432", "gsc12", "l476f32")
 INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}
 
 
@@ -67,7 +67,7 @@ def test_port_matches_golden_int8_classifier(name):
     g = golden(name)
     port = PortOracle(name)
     probs, tens = port.run_inference(g["nn_features"], want_tensors=True)
-    assert np.array_equal(probs, g["nn_probs"])
+    assert same_floats(probs, g["nn_probs"])
     nt = port.n_tensors
     for k, (lo, hi) in INTACT.items():
         got = np.stack([t[k][lo:hi] for t in tens])
@@ -107,7 +107,7 @@ def test_oversized_signal_is_a_dsp_error(synth):
     assert rc == -5
 
 
-@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12")), reason="reference build (oracle/_ref) not present")
+@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12") and have_ref("l476f32")), reason="reference build (oracle/_ref) not present")
 @pytest.mark.parametrize("name", MODELS)
 def test_port_matches_reference_live(name, synth):
     ref, port = RefOracle(name), PortOracle(name)
@@ -117,4 +117,4 @@ def test_port_matches_reference_live(name, synth):
     assert np.array_equal(ref.run_classifier_i16(clips), port.run_classifier_i16(clips))
     rng = np.random.default_rng(7)
     F = rng.normal(0, 2.0, (64, 637)).astype(np.float32)
-    assert np.array_equal(ref.run_inference(F), port.run_inference(F))
+    assert same_floats(ref.run_inference(F), port.run_inference(F))

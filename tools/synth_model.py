@@ -7,6 +7,8 @@ include-path-relative includes) IN THE SAME GENERATED-FILE FORMAT, so that
 very same Register_*/trained_model_init boundary as a real Edge Impulse export.
 
     python tools/synth_model.py <L432 export root> <out dir>
+    python tools/synth_model.py --float <L432 export root (template)> <L476 export root (weights)> <out dir>
+      -> BASELINE config 5: float32 twin of the L476 model (weights dequantised, all tensors kTfLiteFloat32)
 
 Nothing from the reference is stored in this repo: its generated files are read as TEMPLATES at generation time and
 only the data tables are substituted (regex), the result is written under the (git-ignored) output directory:
@@ -82,6 +84,81 @@ def set_arena_tensor_bytes(text, dim_idx, nbytes):
     return new
 
 
+def get_int_array(text, idx):
+    m = re.search(r"const ALIGN\(8\) \w+ tensor_data%d\[[^\]]*\] = \{(.*?)\};" % idx, text, flags=re.S)
+    body = re.sub(r"/\*.*?\*/", " ", m.group(1), flags=re.S)  # generated files annotate rows with /* [i][j][][] */
+    return np.array([int(v) for v in body.replace("\n", " ").split(",") if v.strip()], np.int64)
+
+
+def fmt_f32_array(a, per_line=8):
+    a = [np.float32(v) for v in a]
+    lines = [", ".join("%.9g" % float(v) for v in a[i:i + per_line]) + ", " for i in range(0, len(a), per_line)]
+    return "{ \n  " + "\n  ".join(lines) + "\n}"
+
+
+def main_float(template_root, weights_root, out_root):
+    """BASELINE config 5: float32 twin of the int8 model under <weights_root> (same topology): w = scale_c * q,
+    biases b = scale * q, all tensors kTfLiteFloat32, no quantisation, arena re-planned without aliasing."""
+    cpp = open(os.path.join(template_root, "tflite-model", "trained_model_compiled.cpp")).read()
+    src = open(os.path.join(weights_root, "tflite-model", "trained_model_compiled.cpp")).read()
+    hdr = open(os.path.join(template_root, "tflite-model", "trained_model_compiled.h")).read()
+    meta = open(os.path.join(template_root, "model-parameters", "model_metadata.h")).read()
+    src_meta = open(os.path.join(weights_root, "model-parameters", "model_metadata.h")).read()
+    blocks = open(os.path.join(template_root, "model-parameters", "dsp_blocks.h")).read()
+    n_labels = int(re.search(r"#define EI_CLASSIFIER_LABEL_COUNT\s+(\d+)", src_meta).group(1))
+    labels = re.search(r"ei_classifier_inferencing_categories\[\] = \{([^}]*)\}", src_meta).group(1)
+    dims = {2: "30", 3: "10", 4: str(n_labels), 5: f"{n_labels}*10", 6: "30", 7: "30*1*7*13", 8: "10", 9: "10*1*7*30"}
+    per_channel = {7: 7 * 13, 9: 7 * 30, 6: 1, 8: 1}  # elements per output channel for per-channel scaled tensors
+    for idx in (2, 3, 4, 5, 6, 7, 8, 9):
+        q = get_int_array(src, idx).astype(np.float32)
+        sc = get_scales(src, idx).astype(np.float32)
+        if len(sc) > 1:
+            sc = np.repeat(sc, per_channel[idx])
+        vals = (sc * q).astype(np.float32)  # float32 product, the value a float model would hold
+        pat = r"const ALIGN\(8\) \w+ tensor_data%d\[[^\]]*\] = \{.*?\};" % idx
+        cpp = sub_one(pat, f"const ALIGN(8) float tensor_data{idx}[{dims[idx]}] = {fmt_f32_array(vals)};", cpp)
+    cpp = set_dims(cpp, 4, [n_labels])
+    cpp = set_dims(cpp, 5, [n_labels, 10])
+    cpp = set_dims(cpp, 29, [1, n_labels])
+    cpp = set_dims(cpp, 30, [1, n_labels])
+    # tensor table: every int8 / quantised int32 tensor becomes float32 without quantisation; arena offsets are
+    # re-planned sequentially (no aliasing), 16-byte aligned
+    elems = {}
+    for m in re.finditer(r"const TfArray<(\d+), int> tensor_dimension(\d+) = \{ \d+, \{ ([^}]*)\} \};", cpp):
+        elems[int(m.group(2))] = int(np.prod([int(v) for v in m.group(3).split(",")]))
+    off = 0
+
+    def row(m):
+        nonlocal off
+        alloc, typ, place, dim, nbytes, quant = m.group(1), m.group(2), m.group(3), int(m.group(4)), int(m.group(5)), m.group(6)
+        is_float = typ == "kTfLiteInt8" or (typ == "kTfLiteInt32" and "Affine" in quant)
+        if is_float:
+            typ, nbytes, quant = "kTfLiteFloat32", 4 * elems[dim], "{kTfLiteNoQuantization, nullptr}"
+        if alloc == "kTfLiteArenaRw":
+            place = f"tensor_arena + {off}"
+            off += (nbytes + 15) // 16 * 16
+        return f"{{ {alloc}, {typ}, {place}, (TfLiteIntArray*)&tensor_dimension{dim}, {nbytes}, {quant}, }}"
+
+    cpp, n = re.subn(r"\{ (kTfLite\w+), (kTfLite\w+), ([^,]+), \(TfLiteIntArray\*\)&tensor_dimension(\d+), (\d+), (\{kTfLite\w+, [^}]*\}), \}", row, cpp)
+    assert n == 31, n
+    cpp = sub_one(r"constexpr int kTensorArenaSize = \d+;", f"constexpr int kTensorArenaSize = {off + 8192};", cpp)
+    meta = sub_one(r"#define EI_CLASSIFIER_LABEL_COUNT\s+\d+", f"#define EI_CLASSIFIER_LABEL_COUNT                {n_labels}", meta)
+    meta = sub_one(r"const char\* ei_classifier_inferencing_categories\[\] = \{[^}]*\};",
+                   "const char* ei_classifier_inferencing_categories[] = {" + labels + "};", meta)
+    for key, val in (("EI_CLASSIFIER_TFLITE_INPUT_DATATYPE", "EI_CLASSIFIER_DATATYPE_FLOAT32"), ("EI_CLASSIFIER_TFLITE_INPUT_QUANTIZED", "0"),
+                     ("EI_CLASSIFIER_TFLITE_OUTPUT_DATATYPE", "EI_CLASSIFIER_DATATYPE_FLOAT32"), ("EI_CLASSIFIER_TFLITE_OUTPUT_QUANTIZED", "0")):
+        meta = sub_one(r"#define %s\s+\S+" % key, f"#define {key}      {val}", meta)
+    # keep the DSP block of the weights' model (low/high frequency etc.)
+    cfg = re.search(r"ei_dsp_config_mfcc_t \w+ = \{(.*?)\};", src_meta, flags=re.S).group(1)
+    meta = sub_one(r"(ei_dsp_config_mfcc_t \w+ = \{).*?(\};)", re.search(r"ei_dsp_config_mfcc_t \w+ = \{", meta).group(0) + cfg + "};", meta)
+    for sub, name, text in (("tflite-model", "trained_model_compiled.cpp", cpp), ("tflite-model", "trained_model_compiled.h", hdr),
+                            ("model-parameters", "model_metadata.h", meta), ("model-parameters", "dsp_blocks.h", blocks)):
+        os.makedirs(os.path.join(out_root, sub), exist_ok=True)
+        with open(os.path.join(out_root, sub, name), "w") as f:
+            f.write(text)
+    print("synthesised float32 twin under", out_root, "arena", off + 8192)
+
+
 def main(src_root, out_root):
     rng = np.random.default_rng(SEED)
     n = len(LABELS)
@@ -127,6 +204,9 @@ def main(src_root, out_root):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) != 3:
+    if len(sys.argv) == 5 and sys.argv[1] == "--float":  # --float <template export (L432 style)> <weights export> <out>
+        main_float(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif len(sys.argv) == 3:
+        main(sys.argv[1], sys.argv[2])
+    else:
         sys.exit(__doc__)
-    main(sys.argv[1], sys.argv[2])
