@@ -59,12 +59,19 @@ def load_library() -> C.CDLL:
     L.eikws_infer_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_taps_i16_device.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.eikws_synth_i16_device.argtypes = [vp, vp, sz, u64, u64, vp]
+    L.eikws_decimate_i2s_device.argtypes = [vp, vp, sz, i32, i32, vp, vp]
     L.eikws_classify_i16_host.argtypes = [vp, vp, sz, vp]
     L.eikws_classify_f32_host.argtypes = [vp, vp, sz, vp]
     L.eikws_features_i16_host.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_f32_host.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_infer_host.argtypes = [vp, vp, sz, vp]
     L.eikws_classify_taps_i16_host.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.eikws_streams_create.argtypes = [vp, sz, i32, C.POINTER(vp)]
+    L.eikws_streams_destroy.argtypes = [vp]
+    L.eikws_streams_reset.argtypes = [vp]
+    L.eikws_streams_slice_size.argtypes = [vp]
+    L.eikws_streams_push_i16_host.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32)]
+    L.eikws_streams_push_i16_device.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32), vp]
     L.eikws_debug_host_plan.argtypes = [C.c_char_p, sz, vp, vp, vp, i32, C.POINTER(i32)]
     _lib = L
     return L
@@ -199,12 +206,66 @@ class Impulse:
         _check(self._lib.eikws_infer_device(self._h, C.c_void_p(features.data_ptr()), n, C.c_void_p(out.data_ptr()), stream))
         return out
 
+    def decimate_i2s_device(self, i2s, n_out, skip=4, shift=8):
+        """firmware microphone path (main.cpp:507-521): int32 SAI words -> int16 16 kHz mono, pcm[i] = i2s[skip*i] >> shift"""
+        import torch
+        assert i2s.is_cuda and i2s.dtype == torch.int32 and i2s.is_contiguous() and i2s.numel() >= skip * n_out
+        out = torch.empty(n_out, dtype=torch.int16, device=i2s.device)
+        stream = C.c_void_p(torch.cuda.current_stream(i2s.device).cuda_stream)
+        _check(self._lib.eikws_decimate_i2s_device(self._h, C.c_void_p(i2s.data_ptr()), n_out, skip, shift, C.c_void_p(out.data_ptr()), stream))
+        return out
+
     def synth_clips_device(self, n_clips, first_clip=0, seed=0xE1D5):
         import torch
         out = torch.empty((n_clips, self.raw_sample_count), dtype=torch.int16, device=f"cuda:{self.device}")
         stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
         _check(self._lib.eikws_synth_i16_device(self._h, C.c_void_p(out.data_ptr()), n_clips, first_clip, seed, stream))
         return out
+
+
+class Streams:
+    """run_classifier_continuous over `n_streams` concurrent audio streams (one slice per stream per push)."""
+
+    def __init__(self, impulse: "Impulse", n_streams: int, slices_per_window: int = 4):
+        self._lib = load_library()
+        self.impulse = impulse
+        self.n_streams = n_streams
+        h = C.c_void_p()
+        _check(self._lib.eikws_streams_create(impulse._h, n_streams, slices_per_window, C.byref(h)))
+        self._s = h
+        self.slice_size = self._lib.eikws_streams_slice_size(h)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.eikws_streams_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(self._lib.eikws_streams_reset(self._s))
+
+    def push(self, slices: np.ndarray, beyond: float = 0.0):
+        """slices [n_streams, slice_size] int16 -> probabilities [n_streams, labels] (moving-average filtered) or None
+        while the feature window is still filling"""
+        slices = np.ascontiguousarray(slices, dtype=np.int16).reshape(self.n_streams, self.slice_size)
+        probs = np.zeros((self.n_streams, self.impulse.label_count), np.float32)
+        has = C.c_int(0)
+        _check(self._lib.eikws_streams_push_i16_host(self._s, _np_ptr(slices), C.c_float(beyond), _np_ptr(probs), C.byref(has)))
+        return probs if has.value else None
+
+    def push_device(self, slices, probs, beyond: float = 0.0) -> bool:
+        import torch
+        assert slices.is_cuda and slices.dtype == torch.int16 and slices.is_contiguous()
+        has = C.c_int(0)
+        stream = C.c_void_p(torch.cuda.current_stream(slices.device).cuda_stream)
+        _check(self._lib.eikws_streams_push_i16_device(self._s, C.c_void_p(slices.data_ptr()), C.c_float(beyond), C.c_void_p(probs.data_ptr()),
+                                                       C.byref(has), stream))
+        return bool(has.value)
 
 
 def debug_host_plan(model="l476"):

@@ -264,6 +264,17 @@ int eikws_classify_taps_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t
     return launch(h, d_pcm, false, nullptr, n, true, d_probs, d_features, d_q, static_cast<cudaStream_t>(stream));
 }
 
+// Core/Src/main.cpp:507-521: pcm[i] = (int16_t)(i2s[skip * i] >> shift)   (firmware: skip 4, shift 8)
+int eikws_decimate_i2s_device(eikws_handle *h, const int32_t *d_i2s, size_t n_out, int skip, int shift, int16_t *d_pcm, void *stream) {
+    if (!h || !d_i2s || !d_pcm || skip < 1 || shift < 0 || shift > 31) return fail(EIKWS_ERR_BAD_ARG, "bad argument");
+    if (reinterpret_cast<uintptr_t>(d_pcm) & 15) return fail(EIKWS_ERR_BAD_ARG, "output buffer must be 16-byte aligned");
+    DeviceGuard guard(h->device);
+    cudaError_t e = launch_decimate_i2s(d_i2s, n_out, skip, shift, d_pcm, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "decimate launch");
+    h->launches++;
+    return EIKWS_OK;
+}
+
 int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n, uint64_t first_clip, uint64_t seed, void *stream) {
     if (!h || !d_pcm) return fail(EIKWS_ERR_BAD_ARG, "null argument");
     DeviceGuard guard(h->device);
@@ -390,6 +401,168 @@ int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_
     }
     if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
     return eikws_features_f32_host(h, h->h_pinned, 1, features, nullptr);
+}
+
+// ---- continuous mode: many audio streams advancing one slice per call ---------------------------------------------
+// run_classifier_continuous (ei_run_classifier.h:184-282).  The reference serves ONE stream with static state; here
+// n_streams streams advance in lock step, so the bookkeeping the reference keeps in statics (slice_offset,
+// feature_buffer_full :116-121, extract_mfcc_per_slice_features' first_run ei_run_dsp.h:313, the MAF index) is shared.
+struct eikws_streams {
+    eikws_handle *h = nullptr;
+    size_t n = 0;
+    int slices = 4, slice_size = 0, maf_len = 2;
+    bool first_run = false, window_full = false;
+    size_t slice_offset = 0;
+    int maf_idx = 0;
+    float *d_features = nullptr, *d_maf_buf = nullptr, *d_maf_sum = nullptr;
+    int16_t *d_slices = nullptr;  // staging for the host entry point
+    float *d_probs = nullptr;
+};
+
+void eikws_streams_destroy(eikws_streams *s) {
+    if (!s) return;
+    DeviceGuard guard(s->h->device);
+    if (s->d_features) cudaFree(s->d_features);
+    if (s->d_maf_buf) cudaFree(s->d_maf_buf);
+    if (s->d_maf_sum) cudaFree(s->d_maf_sum);
+    if (s->d_slices) cudaFree(s->d_slices);
+    if (s->d_probs) cudaFree(s->d_probs);
+    delete s;
+}
+
+// power-up state: run_classifier_init (:164-172) plus what the reference can only reset by restarting
+int eikws_streams_reset(eikws_streams *s) {
+    if (!s) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(s->h->device);
+    const size_t L = s->h->graph.labels.size();
+    cudaError_t e;
+    if ((e = cudaMemset(s->d_features, 0, s->n * kFeatures * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    if ((e = cudaMemset(s->d_maf_buf, 0, s->n * L * s->maf_len * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    if ((e = cudaMemset(s->d_maf_sum, 0, s->n * L * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    s->first_run = false;
+    s->window_full = false;
+    s->slice_offset = 0;
+    s->maf_idx = 0;
+    return EIKWS_OK;
+}
+
+int eikws_streams_create(eikws_handle *h, size_t n_streams, int slices_per_window, eikws_streams **out) {
+    if (!h || !out || n_streams == 0 || slices_per_window < 2 || kSamples % slices_per_window) return fail(EIKWS_ERR_BAD_ARG, "bad argument");
+    *out = nullptr;
+    if (!h->host.dev.nn.fused.enabled) return fail(EIKWS_ERR_UNSUPPORTED, "continuous mode needs the fused int8 classifier plan");
+    const int slice = kSamples / slices_per_window;
+    if ((slice * 2) % 16 || slice < 2 * kFrameLen) return fail(EIKWS_ERR_UNSUPPORTED, "unsupported slice size");
+    eikws_streams *s = new (std::nothrow) eikws_streams();
+    if (!s) return fail(EIKWS_ERR_ALLOC_FAILED, "out of memory");
+    s->h = h;
+    s->n = n_streams;
+    s->slices = slices_per_window;
+    s->slice_size = slice;
+    s->maf_len = slices_per_window >> 1;
+    DeviceGuard guard(h->device);
+    const size_t L = h->graph.labels.size();
+    cudaError_t e;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&s->d_features), n_streams * kFeatures * 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_maf_buf), n_streams * L * s->maf_len * 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&s->d_maf_sum), n_streams * L * 4)) != cudaSuccess) {
+        eikws_streams_destroy(s);
+        return cuda_fail(e, "cudaMalloc(stream state)");
+    }
+    int rc = eikws_streams_reset(s);
+    if (rc) {
+        eikws_streams_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return EIKWS_OK;
+}
+
+int eikws_streams_slice_size(const eikws_streams *s) { return s ? s->slice_size : 0; }
+
+// One slice for every stream.  d_slices [n_streams][slice_size] int16, d_probs [n_streams][labels] (written only when
+// *has_result becomes 1: the window is full and the values are the moving-average-filtered probabilities).
+// `beyond` = the float the application's callback returns for indices past the slice (the reference reads one such
+// sample per slice, see oracle/ref_harness.cpp); a zero-padded buffer gives 0.
+static int streams_push_device(eikws_streams *s, const void *d_slices, bool f32, float beyond, float *d_probs, int *has_result, void *stream) {
+    if (!s || !d_slices || !d_probs || !has_result) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    if (reinterpret_cast<uintptr_t>(d_slices) & 15) return fail(EIKWS_ERR_BAD_ARG, "slice buffer must be 16-byte aligned");
+    eikws_handle *h = s->h;
+    DeviceGuard guard(h->device);
+    const MfccConfig &c = h->graph.mfcc;
+    int total_length = s->slice_size;
+    if (s->first_run) total_length += static_cast<int>(c.frame_length * static_cast<float>(c.sample_rate));  // ei_run_dsp.h:322-324
+    s->first_run = true;
+    const int n_frames = (total_length - kFrameLen) / kFrameStride;  // calculate_no_of_stack_frames (processing.hpp:260-284)
+    const size_t feature_size = static_cast<size_t>(n_frames) * kCepstra;
+    if (s->slice_offset + feature_size > kFeatures) return fail(EIKWS_ERR_DSP, "Would write outside feature buffer");
+    const size_t offset_now = s->slice_offset;
+    if (!s->window_full) {  // ei_run_classifier.h:230-238
+        s->slice_offset += feature_size;
+        if (s->slice_offset > kFeatures - feature_size) {
+            s->window_full = true;
+            s->slice_offset -= feature_size;
+        }
+    }
+    ContinuousArgs a;
+    a.plan = h->dev.d_plan;
+    a.slices = d_slices;
+    a.input_is_f32 = f32;
+    a.slice_size = s->slice_size;
+    a.n_frames = n_frames;
+    a.total_length = total_length;
+    a.beyond = beyond;
+    a.n_streams = s->n;
+    a.state_features = s->d_features;
+    a.maf_buf = s->d_maf_buf;
+    a.maf_sum = s->d_maf_sum;
+    a.slice_offset = static_cast<int>(offset_now);
+    a.window_full = s->window_full ? 1 : 0;
+    a.maf_idx = s->maf_idx;
+    a.maf_len = s->maf_len;
+    a.probs = d_probs;
+    a.sm_count = h->sm_count;
+    size_t g = static_cast<size_t>(h->sm_count) * 4;
+    a.grid = static_cast<int>(s->n < g ? s->n : g);
+    a.stream = static_cast<cudaStream_t>(stream);
+    cudaError_t e = launch_continuous(a);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    h->launches++;
+    *has_result = s->window_full ? 1 : 0;
+    if (s->window_full && ++s->maf_idx >= s->maf_len) s->maf_idx = 0;
+    return EIKWS_OK;
+}
+
+int eikws_streams_push_i16_device(eikws_streams *s, const int16_t *d_slices, float beyond, float *d_probs, int *has_result, void *stream) {
+    return streams_push_device(s, d_slices, false, beyond, d_probs, has_result, stream);
+}
+int eikws_streams_push_f32_device(eikws_streams *s, const float *d_slices, float beyond, float *d_probs, int *has_result, void *stream) {
+    return streams_push_device(s, d_slices, true, beyond, d_probs, has_result, stream);
+}
+
+static int streams_push_host(eikws_streams *s, const void *slices, bool f32, float beyond, float *probs, int *has_result) {
+    if (!s || !slices || !probs || !has_result) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    eikws_handle *h = s->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t L = h->graph.labels.size(), bytes = s->n * static_cast<size_t>(s->slice_size) * (f32 ? 4 : 2);
+    cudaError_t e;
+    if (!s->d_slices && (e = cudaMalloc(reinterpret_cast<void **>(&s->d_slices), s->n * static_cast<size_t>(s->slice_size) * 4)) != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc");
+    if (!s->d_probs && (e = cudaMalloc(reinterpret_cast<void **>(&s->d_probs), s->n * L * 4)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemcpyAsync(s->d_slices, slices, bytes, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return cuda_fail(e, "H2D slices");
+    int rc = streams_push_device(s, s->d_slices, f32, beyond, s->d_probs, has_result, h->stream);
+    if (rc) return rc;
+    if (*has_result && (e = cudaMemcpyAsync(probs, s->d_probs, s->n * L * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+        return cuda_fail(e, "D2H probs");
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
+    return EIKWS_OK;
+}
+
+int eikws_streams_push_i16_host(eikws_streams *s, const int16_t *slices, float beyond, float *probs, int *has_result) {
+    return streams_push_host(s, slices, false, beyond, probs, has_result);
+}
+int eikws_streams_push_f32_host(eikws_streams *s, const float *slices, float beyond, float *probs, int *has_result) {
+    return streams_push_host(s, slices, true, beyond, probs, has_result);
 }
 
 // stage taps of the fused kernel for parity debugging (tests only): per clip P[129][49] (transposed power spectra),

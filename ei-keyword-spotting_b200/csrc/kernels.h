@@ -30,6 +30,25 @@ struct LaunchArgs {
 };
 
 cudaError_t launch_run_classifier(const LaunchArgs &a);
+
+// one slice for every stream (run_classifier_continuous); requires the fused int8 classifier plan
+struct ContinuousArgs {
+    const DevPlan *plan = nullptr;
+    const void *slices = nullptr;     // device: [n_streams][slice_size] int16 or float
+    bool input_is_f32 = false;
+    int slice_size = 0, n_frames = 0, total_length = 0;
+    float beyond = 0.0f;
+    size_t n_streams = 0;
+    float *state_features = nullptr;  // device: [n_streams][637]
+    float *maf_buf = nullptr;         // device: [n_streams][labels][maf_len]
+    float *maf_sum = nullptr;         // device: [n_streams][labels]
+    int slice_offset = 0, window_full = 0, maf_idx = 0, maf_len = 1;
+    float *probs = nullptr;           // device: [n_streams][labels]
+    int grid = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+};
+cudaError_t launch_continuous(const ContinuousArgs &a);
+cudaError_t launch_decimate_i2s(const int32_t *i2s, size_t n_out, int skip, int shift, int16_t *pcm, cudaStream_t st);
 cudaError_t launch_synth(int16_t *pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, cudaStream_t st);
 int kernel_threads();
 int debug_tap_floats();  // P[129][49] + logmel[49][33] + cepstra[49][13]

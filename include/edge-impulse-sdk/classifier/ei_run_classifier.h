@@ -144,8 +144,49 @@ static int eikws_dropin_extract_mfcc(ei::signal_t *signal, ei::matrix_t *output_
 
 namespace {
 
-/* reference :164-172 -- resets the continuous-mode state; the one-shot path is stateless */
-extern "C" void run_classifier_init(void) {}
+/* continuous mode state of the (single) stream this process serves, like the reference's statics (:116-121, :187) */
+static eikws_streams *eikws_dropin_stream = NULL;
+static bool eikws_dropin_stream_started = false;
+
+/* reference :164-172.  Note: the reference's init leaves extract_mfcc_per_slice_features' `first_run` and the feature
+ * window untouched (they can only be reset by a restart); here init returns the stream to its power-up state. */
+extern "C" void run_classifier_init(void) {
+    if (eikws_dropin_stream) eikws_streams_reset(eikws_dropin_stream);
+    eikws_dropin_stream_started = false;
+}
+
+/* reference :184-282: one slice (EI_CLASSIFIER_SLICE_SIZE samples) per call; result is filled once the 1-second window
+ * is full (values are the moving-average-filtered probabilities), otherwise left untouched like the reference does. */
+extern "C" EI_IMPULSE_ERROR run_classifier_continuous(signal_t *signal, ei_impulse_result_t *result, bool debug = false) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
+    if (!eikws_dropin_stream && eikws_streams_create(h, 1, EI_CLASSIFIER_SLICES_PER_MODEL_WINDOW, &eikws_dropin_stream) != EIKWS_OK) {
+        ei_printf("ERR: eikws-b200 continuous mode: %s\n", eikws_last_error());
+        return EI_IMPULSE_ALLOC_FAILED;
+    }
+    if (signal->total_length != (size_t)EI_CLASSIFIER_SLICE_SIZE) return EI_IMPULSE_DSP_ERROR;
+    static float slice[EI_CLASSIFIER_SLICE_SIZE];
+    uint64_t t0 = ei_read_timer_ms();
+    if (signal->get_data(0, EI_CLASSIFIER_SLICE_SIZE, slice) != 0) return EI_IMPULSE_DSP_ERROR;
+    float beyond = 0.0f;
+    if (eikws_dropin_stream_started) {
+        /* the reference pretends the slice is one frame longer (ei_run_dsp.h:322-324, it mutates the caller's signal_t)
+         * and its pre-emphasis then asks the callback for the LAST sample of that longer signal (processing.hpp:68) */
+        const ei_dsp_config_mfcc_t *c = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
+        signal->total_length += (size_t)(c->frame_length * (float)EI_CLASSIFIER_FREQUENCY);
+        if (signal->get_data(signal->total_length - 1, 1, &beyond) != 0) return EI_IMPULSE_DSP_ERROR;
+    }
+    eikws_dropin_stream_started = true;
+    float values[EI_CLASSIFIER_LABEL_COUNT];
+    int has_result = 0;
+    int rc = eikws_streams_push_f32_host(eikws_dropin_stream, slice, beyond, values, &has_result);
+    if (rc != EIKWS_OK) return eikws_dropin_error(rc);
+    result->timing.dsp = (int)(ei_read_timer_ms() - t0);
+    result->timing.classification = 0;
+    if (has_result) eikws_dropin_fill_result(result, values, debug);
+    if (ei_run_impulse_check_canceled() == EI_IMPULSE_CANCELED) return EI_IMPULSE_CANCELED;
+    return EI_IMPULSE_OK;
+}
 
 /* reference :293-641: classify an already-extracted feature matrix */
 extern "C" EI_IMPULSE_ERROR run_inference(ei::matrix_t *fmatrix, ei_impulse_result_t *result, bool debug = false) {

@@ -116,6 +116,32 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
 /* extract_mfcc_features (ei_run_dsp.h:256-308) for one clip pulled through the same callback: features[feature_count] */
 int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *features);
 
+/* ---- continuous mode: run_classifier_continuous (ei_run_classifier.h:184-282) over many streams --------------
+ * Every call feeds ONE slice (raw_sample_count / slices_per_window samples) of every stream; all streams advance in
+ * lock step.  Per stream the semantics are those of one reference process from power-up: per-slice MFCC without CMVN
+ * (extract_mfcc_per_slice_features, ei_run_dsp.h:310-366), a 637-feature window, CMVN + classifier over the whole
+ * window once it is full, a moving average over slices_per_window/2 results (run_moving_average_filter :134-145).
+ * `beyond`: from the second slice on the reference asks the signal callback for ONE sample past the end of the slice
+ * (index slice_size + 319); pass the float that callback returns there (a zero-padded buffer: 0). */
+typedef struct eikws_streams eikws_streams;
+int eikws_streams_create(eikws_handle *h, size_t n_streams, int slices_per_window, eikws_streams **out);
+void eikws_streams_destroy(eikws_streams *s);
+int eikws_streams_reset(eikws_streams *s); /* run_classifier_init (:164-172) + power-up */
+int eikws_streams_slice_size(const eikws_streams *s);
+/* d_slices [n_streams][slice_size] int16 (device, 16-byte aligned); d_probs [n_streams][label_count] is written and
+ * *has_result set to 1 only once the window is full */
+int eikws_streams_push_i16_device(eikws_streams *s, const int16_t *d_slices, float beyond, float *d_probs, int *has_result, void *stream);
+int eikws_streams_push_i16_host(eikws_streams *s, const int16_t *slices, float beyond, float *probs, int *has_result);
+/* same with float samples as the signal callback delivers them */
+int eikws_streams_push_f32_device(eikws_streams *s, const float *d_slices, float beyond, float *d_probs, int *has_result, void *stream);
+int eikws_streams_push_f32_host(eikws_streams *s, const float *slices, float beyond, float *probs, int *has_result);
+
+/* ---- caller-side ingest ----------------------------------------------------------------------------------------
+ * The firmware's microphone path (nucleo-l476-keyword-spotting/Core/Src/main.cpp:507-521): SAI words (32 kHz stereo,
+ * 24 valid bits in 32) -> 16 kHz mono int16: d_pcm[i] = (int16_t)(d_i2s[skip * i] >> shift); firmware: skip 4, shift 8.
+ * d_pcm must be 16-byte aligned; d_i2s holds at least skip * n_out words. */
+int eikws_decimate_i2s_device(eikws_handle *h, const int32_t *d_i2s, size_t n_out, int skip, int shift, int16_t *d_pcm, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *eikws_last_error(void); /* thread-local text of the last failure */
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim) */

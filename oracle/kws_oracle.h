@@ -56,6 +56,15 @@ int kws_model_tensor_bytes(const kws_model *m, int i);
 int kws_oracle_run_classifier_i16(const kws_model *m, const int16_t *pcm, int n, float *probs, float *features_out);
 int kws_oracle_run_classifier_f32(const kws_model *m, const float *x, int n, float *probs, float *features_out);
 
+/* ---- continuous mode: run_classifier_continuous (ei_run_classifier.h:184-282) for ONE stream from power-up ---- */
+typedef struct kws_stream kws_stream;
+kws_stream *kws_stream_new(const kws_model *m, int slices_per_window); /* EI_CLASSIFIER_SLICES_PER_MODEL_WINDOW (4) */
+void kws_stream_free(kws_stream *s);
+int kws_stream_slice_size(const kws_stream *s);
+/* one slice of slice_size samples; `beyond` = what the signal callback returns for indices past the slice (see
+ * oracle/ref_harness.cpp); *has_result = 1 once the feature window is full (probs are the MAF-filtered values) */
+int kws_stream_push_i16(kws_stream *s, const int16_t *slice, int16_t beyond, float *probs, int *has_result);
+
 #ifdef __cplusplus
 }
 #endif

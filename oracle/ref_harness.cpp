@@ -229,6 +229,31 @@ int ref_rfft_mag(const float *frame, int frame_len, int n_fft, float *out) {
     return ei::numpy::rfft(frame, frame_len, out, n_fft / 2 + 1, n_fft);
 }
 
+// ---- continuous mode (run_classifier_continuous, ei_run_classifier.h:184-282) -------------------------------
+// One call = one slice of EI_CLASSIFIER_SLICE_SIZE samples.  The reference keeps its state in statics that
+// run_classifier_init() only partly resets (extract_mfcc_per_slice_features' `first_run`, ei_run_dsp.h:313, and the
+// feature matrix are never reset), so one loaded copy of this library models exactly ONE stream from power-up.
+// From the second slice on the reference asks the callback for sample total_length-1 = SLICE_SIZE+319, i.e. beyond
+// the slice (ei_run_dsp.h:322-324 + processing.hpp:68); the firmware then reads past its buffer.  Here the slice is
+// staged in a buffer whose tail [SLICE_SIZE, SLICE_SIZE+320) holds `beyond` (as int16), which makes that read defined.
+static int16_t g_slice_buf[EI_CLASSIFIER_SLICE_SIZE + 1024];
+int ref_slice_size() { return EI_CLASSIFIER_SLICE_SIZE; }
+int ref_run_classifier_continuous_i16(const int16_t *slice, int16_t beyond, float *probs, int *has_result) {
+    memcpy(g_slice_buf, slice, sizeof(int16_t) * EI_CLASSIFIER_SLICE_SIZE);
+    for (int i = EI_CLASSIFIER_SLICE_SIZE; i < EI_CLASSIFIER_SLICE_SIZE + 1024; i++) g_slice_buf[i] = beyond;
+    g_pcm = g_slice_buf;
+    signal_t sig;
+    sig.total_length = EI_CLASSIFIER_SLICE_SIZE;
+    sig.get_data = &get_data_i16;
+    ei_impulse_result_t res;
+    memset(&res, 0, sizeof(res));
+    for (int i = 0; i < EI_CLASSIFIER_LABEL_COUNT; i++) res.classification[i].value = -1.0f;  // untouched until the window is full
+    EI_IMPULSE_ERROR e = run_classifier_continuous(&sig, &res, false);
+    *has_result = res.classification[0].value >= 0.0f;
+    for (int i = 0; i < EI_CLASSIFIER_LABEL_COUNT; i++) probs[i] = res.classification[i].value;
+    return (int)e;
+}
+
 // CPU timing loop used by bench.py's reference arm: runs run_classifier over
 // `count` clips laid out back to back, returns seconds elapsed.
 double ref_time_run_classifier_i16(const int16_t *pcm, int n, int count, float *probs_last) {

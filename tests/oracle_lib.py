@@ -221,3 +221,54 @@ class PortOracle:
         for i in range(x.shape[0]):
             assert self.lib.kws_oracle_run_classifier_f32(self.m, _p(x[i], C.c_float), N_SAMPLES, _p(probs[i], C.c_float), None) == 0
         return probs
+
+
+class PortStream:
+    """one reference-semantics audio stream (run_classifier_continuous) on the plain-C oracle"""
+
+    def __init__(self, port: PortOracle, slices_per_window: int = 4):
+        self.port = port
+        L = port.lib
+        L.kws_stream_new.restype = C.c_void_p
+        L.kws_stream_new.argtypes = [C.c_void_p, C.c_int]
+        L.kws_stream_free.argtypes = [C.c_void_p]
+        L.kws_stream_push_i16.argtypes = [C.c_void_p, C.POINTER(C.c_int16), C.c_int16, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        self.s = L.kws_stream_new(port.m, slices_per_window)
+        self.slice_size = N_SAMPLES // slices_per_window
+
+    def push(self, slice_i16: np.ndarray, beyond: int = 0):
+        sl = np.ascontiguousarray(slice_i16, dtype=np.int16).reshape(self.slice_size)
+        probs = np.zeros(self.port.n_labels, np.float32)
+        has = C.c_int(0)
+        rc = self.port.lib.kws_stream_push_i16(self.s, _p(sl, C.c_int16), C.c_int16(beyond), _p(probs, C.c_float), C.byref(has))
+        assert rc == 0, rc
+        return probs if has.value else None
+
+    def __del__(self):
+        try:
+            self.port.lib.kws_stream_free(self.s)
+        except Exception:
+            pass
+
+
+class RefStream:
+    """one stream on the unmodified reference: its continuous-mode state lives in statics that cannot be reset, so every
+    stream gets its own private copy of the shared library"""
+
+    def __init__(self, name: str):
+        import shutil
+        import tempfile
+        self._dir = tempfile.mkdtemp(prefix="eikws_refstream_")
+        path = os.path.join(self._dir, "ref.so")
+        shutil.copy(ref_path(name), path)
+        self.lib = C.CDLL(path)
+        self.n_labels = self.lib.ref_label_count()
+        self.slice_size = self.lib.ref_slice_size()
+
+    def push(self, slice_i16: np.ndarray, beyond: int = 0):
+        sl = np.ascontiguousarray(slice_i16, dtype=np.int16).reshape(self.slice_size)
+        probs = np.zeros(self.n_labels, np.float32)
+        has = C.c_int(0)
+        rc = self.lib.ref_run_classifier_continuous_i16(_p(sl, C.c_int16), C.c_int16(beyond), _p(probs, C.c_float), C.byref(has))
+        assert rc == 0, rc
+        return probs if has.value else None

@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "examples", "_build")
 
 
-def _binary(tag):
-    p = os.path.join(BUILD, f"static_buffer_{tag}")
+def _binary(tag, example="static_buffer"):
+    p = os.path.join(BUILD, f"{example}_{tag}")
     if not os.path.isfile(p):
         pytest.skip("examples/_build not present (run __graft_entry__.build() where /root/reference exists)")
     return p
@@ -45,3 +45,22 @@ def test_dropin_run_classifier_matches_oracle(tag, tmp_path, synth):
     labels = re.findall(r"^\s+(\S+): [0-9.]+\s*$", r.stdout, flags=re.M)
     assert labels == port.labels
     assert np.allclose(got, want, atol=5e-6)  # printed with 5 decimals; values are multiples of 1/256
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["l476", "l432"])
+def test_dropin_run_classifier_continuous_matches_oracle(tag, tmp_path, synth):
+    """the firmware main loop (signal_t + run_classifier_continuous per 250 ms slice) against the drop-in header"""
+    from oracle_lib import PortStream
+    audio = synth.synth_clips(3, first_clip=41).reshape(-1)  # 12 slices
+    f = tmp_path / "audio.pcm"
+    audio.tofile(f)
+    r = subprocess.run([_binary(tag, "continuous_stream"), str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = {int(m.group(1)): [float(v) for v in m.group(2).split()] for m in re.finditer(r"^slice (\d+):(.*)$", r.stdout, flags=re.M)}
+    stream = PortStream(PortOracle(tag))
+    for i in range(12):
+        want = stream.push(audio[i * 4000:(i + 1) * 4000])
+        assert (want is None) == (i not in got)
+        if want is not None:
+            assert np.allclose(got[i], want, atol=1e-8)

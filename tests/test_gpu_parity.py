@@ -187,3 +187,43 @@ def test_error_behaviour(eikws, impulses):
     g = golden("l476")
     sil = [str(k) for k in g["special_names"]].index("silence") + int(g["n_synth"])
     assert np.array_equal(np.array(vals[:], np.float32), g["probs"][sil])
+
+
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12"])
+def test_continuous_mode_matches_oracle(name, eikws, impulses, synth):
+    """run_classifier_continuous for 37 concurrent streams x 14 slices against the plain-C oracle, stream by stream"""
+    from oracle_lib import PortStream
+    imp = impulses[name]
+    n_streams, n_slices = 37, 14
+    streams = eikws.Streams(imp, n_streams)
+    assert streams.slice_size == 4000
+    audio = synth.synth_clips(n_streams * 4, first_clip=900).reshape(n_streams, -1)[:, : n_slices * 4000]
+    port = PortOracle(name)
+    oracles = [PortStream(port) for _ in range(n_streams)]
+    for i in range(n_slices):
+        sl = audio[:, i * 4000:(i + 1) * 4000]
+        got = streams.push(sl)
+        want = [o.push(sl[k]) for k, o in enumerate(oracles)]
+        assert (got is None) == (want[0] is None)
+        if got is not None:
+            assert np.array_equal(got, np.stack(want)), f"slice {i}"
+    # reset == power-up: the same audio gives the same answers again
+    streams.reset()
+    again = [streams.push(audio[:, i * 4000:(i + 1) * 4000]) for i in range(5)]
+    oracles = [PortStream(port) for _ in range(n_streams)]
+    want5 = [[o.push(audio[k, i * 4000:(i + 1) * 4000]) for k, o in enumerate(oracles)] for i in range(5)]
+    assert again[2] is None and np.array_equal(again[4], np.stack(want5[4]))
+    streams.close()
+
+
+def test_i2s_decimation_matches_firmware_isr(impulses):
+    """Core/Src/main.cpp:507-521: every 4th 32-bit SAI word, top 16 of 24 bits"""
+    import torch
+    imp = impulses["l476"]
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    for n_out in (16000 * 33 + 5, 7, 8):
+        i2s = torch.randint(-(1 << 23), 1 << 23, (4 * n_out + 3,), dtype=torch.int32, device="cuda:0", generator=g)
+        got = imp.decimate_i2s_device(i2s, n_out)
+        want = (i2s[: 4 * n_out : 4] >> 8).to(torch.int16)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)

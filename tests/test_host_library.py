@@ -75,3 +75,28 @@ def test_synth_is_deterministic_and_mixed(synth):
     big = synth.synth_clips(200, first_clip=100)
     assert (big == 0).all(axis=1).any()                    # silent clips exist in the mixture
     assert (np.abs(big.astype(np.int32)) >= 32767).any()   # saturating clips exist in the mixture
+
+
+def test_wav_ingest_roundtrip(eikws, synth, tmp_path):
+    """PCM_16 / 16 kHz / mono WAV files (what dataset-curation.py writes) -> [n,16000] int16 batches, pad/truncate to 1 s"""
+    import eikws_b200.ingest as ingest
+    clip = synth.synth_clips(1)[0]
+    paths = []
+    for i, n in enumerate((16000, 12000, 20000)):
+        p = str(tmp_path / f"c{i}.wav")
+        ingest.write_wav(p, np.resize(clip, n))
+        paths.append(p)
+    batch = ingest.read_wav_clips(paths)
+    assert batch.shape == (3, 16000) and batch.dtype == np.int16
+    assert np.array_equal(batch[0], clip)
+    assert np.array_equal(batch[1][:12000], clip[:12000]) and np.all(batch[1][12000:] == 0)
+    assert np.array_equal(batch[2], np.resize(clip, 20000)[:16000])
+    import wave
+    bad = str(tmp_path / "bad.wav")
+    with wave.open(bad, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(b"\0" * 400)
+    with pytest.raises(ValueError):
+        ingest.read_wav(bad)

@@ -118,3 +118,23 @@ def test_port_matches_reference_live(name, synth):
     rng = np.random.default_rng(7)
     F = rng.normal(0, 2.0, (64, 637)).astype(np.float32)
     assert same_floats(ref.run_inference(F), port.run_inference(F))
+
+
+@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432")), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ["l476", "l432"])
+def test_continuous_mode_port_matches_reference_live(name, synth):
+    """run_classifier_continuous over 16 slices of one stream: window fill (11+12+12+12 frames), CMVN over the whole
+    window incl. its two never-written zero rows, moving average over 2 results, window shift"""
+    from oracle_lib import PortStream, RefStream
+    ref, port = RefStream(name), PortStream(PortOracle(name))
+    audio = synth.synth_clips(4, first_clip=3).reshape(-1)
+    n_results = 0
+    for i in range(16):
+        sl = audio[i * 4000:(i + 1) * 4000]
+        a, b = ref.push(sl), port.push(sl)
+        assert (a is None) == (b is None)
+        assert (a is None) == (i < 3)  # the 637-feature window is full after the 4th slice
+        if a is not None:
+            assert np.array_equal(a, b)
+            n_results += 1
+    assert n_results == 13
