@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeikws_b200.so")
+LIB_PATH = os.environ.get("EIKWS_B200_LIB") or os.path.join(_HERE, "libeikws_b200.so")  # the override is for A/B timing of kernel builds
 MODELS_DIR = os.path.join(_HERE, "models")
 MODELS = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl", "gsc12": "gsc12_synth.eikwsmdl", "l476f32": "l476_f32_twin.eikwsmdl"}
 
@@ -51,6 +51,7 @@ def load_library() -> C.CDLL:
     L.eikws_launch_count.restype = u64
     L.eikws_launch_count.argtypes = [vp]
     L.eikws_set_ctas_per_sm.argtypes = [vp, i32]
+    L.eikws_set_clips_per_cta.argtypes = [vp, i32]
     L.eikws_set_skew_ns.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
@@ -121,6 +122,9 @@ class Impulse:
     @property
     def launch_count(self) -> int:
         return int(self._lib.eikws_launch_count(self._h))
+
+    def set_clips_per_cta(self, n: int):
+        _check(self._lib.eikws_set_clips_per_cta(self._h, n))
 
     def set_ctas_per_sm(self, n: int):
         _check(self._lib.eikws_set_ctas_per_sm(self._h, n))

@@ -27,7 +27,8 @@ struct eikws_handle {
     HostPlan host;
     DevicePlan dev;
     int sm_count = 148;
-    int ctas_per_sm = 4;
+    int ctas_per_sm = 4;    // clip groups (160 threads each) resident per SM
+    int clips_per_cta = 2;  // clip groups per CTA: 2 CTAs x 2 groups measured best (profiles/r1_ab_clip_groups.txt)
     int skew_ns = 14000;  // start offset between the CTAs that share an SM (see kernels.cu)
     uint64_t launches = 0;
     std::mutex mu;  // serialises the host-buffer and single-clip paths (they share staging buffers)
@@ -105,6 +106,7 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.qfeatures_out = qfeat;
     a.debug_taps = dbg;
     a.grid = grid_for(h, n);
+    a.clips_per_cta = h->clips_per_cta;
     a.sm_count = h->sm_count;
     a.skew_ns = (n >= static_cast<size_t>(h->sm_count) * h->ctas_per_sm * 8) ? h->skew_ns : 0;  // only worth it for long launches
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
@@ -222,6 +224,11 @@ uint64_t eikws_launch_count(const eikws_handle *h) { return h ? h->launches : 0;
 int eikws_set_ctas_per_sm(eikws_handle *h, int n) {  // tuning knob (not in the public header)
     if (!h || n < 1 || n > 8) return EIKWS_ERR_BAD_ARG;
     h->ctas_per_sm = n;
+    return EIKWS_OK;
+}
+int eikws_set_clips_per_cta(eikws_handle *h, int n) {  // tuning knob (not in the public header)
+    if (!h || (n != 1 && n != 2 && n != 4)) return EIKWS_ERR_BAD_ARG;
+    h->clips_per_cta = n;
     return EIKWS_OK;
 }
 int eikws_set_skew_ns(eikws_handle *h, int ns) {  // tuning knob (not in the public header)

@@ -22,7 +22,8 @@ struct LaunchArgs {
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
     float *debug_taps = nullptr;         // device, tests only: [n_clips][debug_tap_floats()] (int16 classify path)
-    int grid = 0;
+    int grid = 0;                        // CTAs if each holds one clip group (launch divides by clips_per_cta)
+    int clips_per_cta = 1;               // 160-thread clip groups per CTA (1, 2 or 4): int16 + fused classifier path only
     int sm_count = 0;                    // SMs of the device (CTA j of an SM = blockIdx / sm_count)
     int skew_ns = 0;                     // start offset between co-resident CTAs (0 = none)
     int nn_smem_bytes = 0;               // activation arena + conv row scratch

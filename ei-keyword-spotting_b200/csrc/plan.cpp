@@ -819,7 +819,9 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             const NnOpDev &fc = nn.ops[6], &sm = nn.ops[7];
             const ConvSrc *cs = find_conv(6);
             ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fu.st[1].out_c && fu.st[1].pool_out == fu.tail_pool && fu.st[1].in_w == fu.st[0].pool_out &&
-                 fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
+                 fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && fc.in_c <= 32 && fu.st[0].in_rows * fu.st[0].cp <= 1024 &&
+                 fu.st[1].in_rows * fu.st[1].cp <= 512 && fc.in_c * fu.tail_pool <= 256 &&  // region S of the kernel's shared memory map
+                 sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
             if (ok) {
                 NnFusedStage &s0 = fu.st[0], &s1 = fu.st[1];
                 s0.in_off = alloc(s0.in_rows * s0.cp);
