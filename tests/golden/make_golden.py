@@ -30,7 +30,10 @@ from oracle_lib import RefOracle  # noqa: E402
 
 N_SYNTH = 40
 GOLDEN_SEED = 0xE1D5
-INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}  # + output-sized 29, 30
+# arena tensors (index: byte range) that no later node overwrites, i.e. that can still be read after invoke;
+# plus the two output-sized tensors at the end of every graph
+INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}     # L476 topology (l476, l432, gsc12, l476f32)
+INTACT_BY_MODEL = {"zip6": {17: (160, 392), 25: (208, 400), 27: (0, 208)}}           # Arduino-zip topology (arena offsets of its generated file)
 
 
 def crafted_features(n_labels_seed: int) -> np.ndarray:
@@ -45,7 +48,7 @@ def crafted_features(n_labels_seed: int) -> np.ndarray:
 
 
 def main():
-    for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32")):
+    for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32", "zip6")):
         ref = RefOracle(name)
         specials = synth.special_clips()
         clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values()))])
@@ -62,7 +65,9 @@ def main():
                    features=feats, probs=probs, mel0=mel0, energy0=en0, mfcc0=mfcc0, filterbank=ref.filterbank(),
                    features_f32in=feats_f32, nn_features=F, nn_probs=nn_probs, labels=np.array(ref.labels))
         n_t = len(tens[0])
-        for k, (lo, hi) in INTACT.items():
+        intact = INTACT_BY_MODEL.get(name, INTACT)
+        out["intact"] = np.array([[k, lo, hi] for k, (lo, hi) in intact.items()], np.int32)
+        for k, (lo, hi) in intact.items():
             out[f"nn_t{k}"] = np.stack([t[k][lo:hi] for t in tens])
         out["nn_t_fc"] = np.stack([t[n_t - 2] for t in tens])
         out["nn_t_out"] = np.stack([t[n_t - 1] for t in tens])

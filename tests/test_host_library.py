@@ -32,6 +32,15 @@ def test_host_plan_filterbank_matches_reference(eikws, name):
     assert np.all((mult >= (1 << 30)) & (mult < (1 << 31))) and np.all(shift <= 0)
 
 
+def test_third_topology_is_lowered_by_the_generic_plan(eikws):
+    """the Arduino-zip model (conv k3 -> pool 2 (SAME, padded) -> conv k3 -> pool 2 -> FC 208 -> 6): not the fused shape, so
+    it exercises the generic op plan built from the captured Register_* graph"""
+    fb, mult, shift = eikws.debug_host_plan("zip6")
+    g = np.load(os.path.join(GOLDEN, "golden_zip6.npz"))
+    assert np.array_equal(fb, g["filterbank"])  # high_frequency 0 -> 8000 Hz, like L432
+    assert len(mult) == 8 + 16 + 6 and np.all(shift <= 0)
+
+
 def test_float_graph_is_lowered(eikws):
     fb, mult, _ = eikws.debug_host_plan("l476f32")  # BASELINE config 5: float32 twin, no requantisation tables
     assert fb.shape == (129, 32) and len(mult) == 0

@@ -8,7 +8,7 @@ import pytest
 from oracle_lib import PortOracle, RefOracle, have_ref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ("l476", "l432", "gsc12", "l476f32")
+MODELS = ("l476", "l432", "gsc12", "l476f32", "zip6")
 INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}
 
 
@@ -69,7 +69,8 @@ def test_port_matches_golden_int8_classifier(name):
     probs, tens = port.run_inference(g["nn_features"], want_tensors=True)
     assert same_floats(probs, g["nn_probs"])
     nt = port.n_tensors
-    for k, (lo, hi) in INTACT.items():
+    intact = {int(k): (int(lo), int(hi)) for k, lo, hi in g["intact"]} if "intact" in g.files else INTACT
+    for k, (lo, hi) in intact.items():
         got = np.stack([t[k][lo:hi] for t in tens])
         assert np.array_equal(got, g[f"nn_t{k}"]), f"tensor {k}"
     assert np.array_equal(np.stack([t[nt - 2] for t in tens]), g["nn_t_fc"])
@@ -107,7 +108,7 @@ def test_oversized_signal_is_a_dsp_error(synth):
     assert rc == -5
 
 
-@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12") and have_ref("l476f32")), reason="reference build (oracle/_ref) not present")
+@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12") and have_ref("l476f32") and have_ref("zip6")), reason="reference build (oracle/_ref) not present")
 @pytest.mark.parametrize("name", MODELS)
 def test_port_matches_reference_live(name, synth):
     ref, port = RefOracle(name), PortOracle(name)
