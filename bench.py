@@ -91,45 +91,63 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 50 ms from just before the warm-up to the end of the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every 5 ms on a host thread, from before the warm-up to the end
+    of the timed region; stop(t0, t1) reports the samples that fall inside the timed region (all samples if the region
+    was shorter than the sampling period).  Falls back to one `nvidia-smi` query when pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
+        self.samples = []  # (t, sm_mhz, reasons bitmask)
+        self.thread = None
+        self.max_mhz = None
+        self._stop = False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
+            def loop():
+                while not self._stop:
+                    try:
+                        self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], None, set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            self.thread = None
+
+    def stop(self, t0=None, t1=None):
+        self._stop = True
+        if self.thread is None:
+            return self._smi_once()
+        self.thread.join(timeout=2)
+        inside = [x for x in self.samples if t0 is not None and t0 <= x[0] <= t1]
+        use = inside if inside else self.samples
+        sm = sorted(x[1] for x in use)
+        mask = 0
+        for x in use:
+            mask |= x[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": [n for n, b in self.REASONS if mask & b],
+                "samples": len(use), "samples_in_timed_region": len(inside), "source": "nvml, 5 ms period"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi after the run (pynvml unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def main():
@@ -155,7 +173,8 @@ def main():
     config = {"workload": f"BASELINE configs[1]: batch {args.clips_per_gpu} synthetic 1-s 16 kHz int16 clips per GPU, "
                           f"L476 4-label int8 model (MFCC+CMVN+int8 CNN fused), inputs ({args.clips_per_gpu * 32000 / 1e9:.2f} GB/GPU) larger than L2",
               "model": {"l476": "l476_yes_no (EON-compiled int8, 4 labels)", "gsc12": "synthesised 12-label int8 model (BASELINE config 4)",
-                        "l476f32": "float32 twin of l476 (BASELINE config 5)", "l432": "l432 (int8, 3 labels)"}[args.model],
+                        "l476f32": "float32 twin of l476 (BASELINE config 5)", "l432": "l432 (int8, 3 labels)",
+                        "zip6": "third shipped model (Arduino zip, int8, 6 labels, generic op plan)"}[args.model],
               "input": "float32 samples" if args.f32_input else "int16 PCM", "clips_per_gpu": args.clips_per_gpu,
               "sharding": f"{n_gpus} independent shard(s), no collective on the data path"}
 
@@ -213,24 +232,26 @@ def main():
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()  # nvidia-smi needs ~0.2 s to come up: started before the warm-up, which runs the same kernel
+        sampler.start()
     for _ in range(args.warmup):
         imp.run_classifier_device(clips, out=probs)
     barrier()
     launches0 = imp.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         imp.run_classifier_device(clips, out=probs)
     ev1.record()
     torch.cuda.synchronize()
+    t_host1 = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = imp.launch_count - launches0
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
     elapsed_ms = float(t.item())
     value = n_gpus * n * args.steps / (elapsed_ms * 1e-3)
 
@@ -263,6 +284,14 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         kernel_ms = elapsed_ms / max(launches, 1)
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch from the committed ncu capture of this kernel, scaled to this batch (int16 fused path only)
+            if args.model == "l476" and not args.f32_input:
+                with open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["dram_bytes_per_clip"] * n, tj["source"]
+        except Exception:
+            pass
         achieved = n * algo_bytes / (kernel_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,8 +300,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * N_SAMPLES * clips.element_size(), "d2h_bytes_per_step": n * imp.label_count * 4,
                         "steps": args.e2e_steps, "api": ("eikws_classify_f32_host" if args.f32_input else "eikws_classify_i16_host") + " (pinned host buffers, 8192-clip chunks on two streams)"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": peak_src, "kernel": "eikws_run_classifier_kernel<int16,mfcc,nn>",
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "eikws_run_classifier_kernel (one launch per step)",
                              "algo_bytes_per_clip": algo_bytes, "kernel_ms": kernel_ms}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
