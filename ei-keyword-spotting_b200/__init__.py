@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EIKWS_B200_LIB") or os.path.join(_HERE, "libeikws_b200.so")  # the override is for A/B timing of kernel builds
 MODELS_DIR = os.path.join(_HERE, "models")
-MODELS = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl", "gsc12": "gsc12_synth.eikwsmdl", "l476f32": "l476_f32_twin.eikwsmdl", "zip6": "zip6_arduino.eikwsmdl"}
+MODELS = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl", "gsc12": "gsc12_synth.eikwsmdl", "l476f32": "l476_f32_twin.eikwsmdl", "zip6": "zip6_arduino.eikwsmdl", "dw3": "dw3_depthwise_synth.eikwsmdl"}
 
 EI_IMPULSE_OK = 0
 EI_IMPULSE_DSP_ERROR = -5

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <deque>
 
 #include "eikws_b200.h"
 #include "kernels.h"
@@ -476,6 +477,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
         std::vector<int32_t> raw_bias, mult, shift;
     };
     std::vector<ConvSrc> conv_src;
+    std::deque<std::vector<int8_t>> dense_filters;  // depthwise filters expanded to dense [out_c][kw][in_c] (stable addresses)
     std::vector<std::pair<int, std::vector<uint8_t>>> lut_src;
     std::vector<int32_t> exp_lut_src;
 
@@ -509,7 +511,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             err = "non-int8 activation tensor";
             return EIKWS_ERR_UNSUPPORTED;
         }
-        if (n.op == kOpConv2D || n.op == kOpFullyConnected) {
+        if (n.op == kOpConv2D || n.op == kOpDepthwiseConv2D || n.op == kOpFullyConnected) {
             const TensorDesc &in = g.tensors[n.inputs[0]], &flt = g.tensors[n.inputs[1]];
             const bool has_bias = n.inputs.size() > 2 && n.inputs[2] >= 0;
             if (off[n.inputs[0]] < 0 || !flt.is_const || flt.type != kI8 || in.type != kI8) {
@@ -524,7 +526,38 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             int32_t lo, hi;
             op.kind = kNnConv1d;
             std::vector<double> eff;  // real multiplier per output channel
-            if (n.op == kOpConv2D) {
+            const int8_t *w = reinterpret_cast<const int8_t *>(flt.data.data());
+            if (n.op == kOpDepthwiseConv2D) {
+                // DepthwiseConvPerChannel (integer_ops/depthwise_conv.h:22-121): output channel oc = m + ic * depth_multiplier
+                // sums filter[0][0][fx][oc] * (x[.][ic] + in_offset) over fx only.  In integer arithmetic that is exactly the
+                // dense 1xk convolution whose filter is zero for every other input channel, so the filter is expanded once
+                // here and the op runs on the conv kernels (a zero weight contributes exactly 0 to acc and to the bias fold).
+                int di[4], df[4], dq[4];
+                dims4(in, di);
+                dims4(flt, df);
+                dims4(out, dq);
+                const int padding = n.params[0], sw = n.params[1], dm = n.params[3], act = n.params[4], dw = n.params[5];
+                if (di[0] != 1 || di[1] != 1 || df[0] != 1 || df[1] != 1 || dq[1] != 1 || dw != 1 || dm < 1 || df[3] != di[3] * dm || dq[3] != df[3]) {
+                    err = "depthwise conv: only 1xk filters over [1,1,W,C] inputs with dilation 1 are implemented";
+                    return EIKWS_ERR_UNSUPPORTED;
+                }
+                op.in_w = di[2];
+                op.in_c = di[3];
+                op.out_w = dq[2];
+                op.out_c = dq[3];
+                op.kw = df[2];
+                op.stride_w = sw;
+                op.pad_w = same_or_valid_pad(padding, sw, dw, di[2], df[2]);
+                activation_range_i8(act, out, &lo, &hi);
+                dense_filters.emplace_back(static_cast<size_t>(op.out_c) * op.kw * op.in_c, static_cast<int8_t>(0));
+                std::vector<int8_t> &dense = dense_filters.back();
+                for (int oc = 0; oc < op.out_c; oc++) {
+                    for (int fx = 0; fx < op.kw; fx++) dense[(static_cast<size_t>(oc) * op.kw + fx) * op.in_c + oc / dm] = w[fx * op.out_c + oc];
+                    const float fs = flt.scales.size() > 1 ? flt.scales[oc] : flt.scales[0];  // per-channel along filter dimension 3
+                    eff.push_back(static_cast<double>(in.scale()) * static_cast<double>(fs) / static_cast<double>(out.scale()));
+                }
+                w = dense.data();
+            } else if (n.op == kOpConv2D) {
                 int di[4], df[4], dq[4];
                 dims4(in, di);
                 dims4(flt, df);
@@ -576,7 +609,6 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             op.act_min = lo;
             op.act_max = hi;
             std::vector<int32_t> packed(static_cast<size_t>(op.out_c) * op.k_words, 0), bias(op.out_c), mult(op.out_c), shift(op.out_c);
-            const int8_t *w = reinterpret_cast<const int8_t *>(flt.data.data());
             const int32_t *bsrc = has_bias ? reinterpret_cast<const int32_t *>(g.tensors[n.inputs[2]].data.data()) : nullptr;
             if (has_bias && (!g.tensors[n.inputs[2]].is_const || g.tensors[n.inputs[2]].type != kI32)) {
                 err = "conv/fc: bias must be a constant int32 tensor";
@@ -718,7 +750,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             exp_lut_src = elut;
             op.in_off = off[n.inputs[0]];
         } else {
-            err = "operator " + std::to_string(n.op) + " is not implemented (supported: RESHAPE, CONV_2D 1xk, ADD const, MAX_POOL_2D, FULLY_CONNECTED, SOFTMAX)";
+            err = "operator " + std::to_string(n.op) + " is not implemented (supported: RESHAPE, CONV_2D 1xk, DEPTHWISE_CONV_2D 1xk, ADD const, MAX_POOL_2D, FULLY_CONNECTED, SOFTMAX)";
             return EIKWS_ERR_UNSUPPORTED;
         }
         op.out_off = other(op.in_off);

@@ -33,7 +33,9 @@ GOLDEN_SEED = 0xE1D5
 # arena tensors (index: byte range) that no later node overwrites, i.e. that can still be read after invoke;
 # plus the two output-sized tensors at the end of every graph
 INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}     # L476 topology (l476, l432, gsc12, l476f32)
-INTACT_BY_MODEL = {"zip6": {17: (160, 392), 25: (208, 400), 27: (0, 208)}}           # Arduino-zip topology (arena offsets of its generated file)
+INTACT_BY_MODEL = {"zip6": {17: (160, 392), 25: (208, 400), 27: (0, 208)},           # Arduino-zip topology (arena offsets of its generated file)
+                   # depthwise variant: its arena is planned without aliasing, every tensor survives
+                   "dw3": {17: (0, 1470), 19: (0, 1470), 21: (0, 210), 23: (0, 210), 25: (0, 210), 27: (0, 30)}}
 
 
 def crafted_features(n_labels_seed: int) -> np.ndarray:
@@ -48,7 +50,7 @@ def crafted_features(n_labels_seed: int) -> np.ndarray:
 
 
 def main():
-    for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32", "zip6")):
+    for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32", "zip6", "dw3")):
         ref = RefOracle(name)
         specials = synth.special_clips()
         clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values()))])

@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 MODELS_DIR = os.path.join(ROOT, "ei-keyword-spotting_b200", "models")
-MODEL_FILES = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl", "gsc12": "gsc12_synth.eikwsmdl", "l476f32": "l476_f32_twin.eikwsmdl", "zip6": "zip6_arduino.eikwsmdl"}
+MODEL_FILES = {"l476": "l476_yes_no.eikwsmdl", "l432": "l432_trick_or_treat.eikwsmdl", "gsc12": "gsc12_synth.eikwsmdl", "l476f32": "l476_f32_twin.eikwsmdl", "zip6": "zip6_arduino.eikwsmdl", "dw3": "dw3_depthwise_synth.eikwsmdl"}
 
 N_SAMPLES = 16000
 N_FEATURES = 637

@@ -12,7 +12,7 @@ from oracle_lib import PortOracle
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ("l476", "l432", "gsc12", "l476f32", "zip6")
+MODELS = ("l476", "l432", "gsc12", "l476f32", "zip6", "dw3")
 FLOAT_MODELS = ("l476f32",)
 PROB_TOL_F32 = 1e-5  # north-star tolerance for the float32 path (GPU expf vs glibc expf in the softmax)
 FEATURE_TOL = 1e-5  # north-star tolerance on the float MFCC coefficients (we additionally assert exact equality)

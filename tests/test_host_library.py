@@ -41,6 +41,12 @@ def test_third_topology_is_lowered_by_the_generic_plan(eikws):
     assert len(mult) == 8 + 16 + 6 and np.all(shift <= 0)
 
 
+def test_depthwise_conv_is_lowered_as_a_sparse_dense_conv(eikws):
+    """DEPTHWISE_CONV_2D: synthesised variant of the L432 graph; 30 + 30 + 3 requantisation channels"""
+    fb, mult, shift = eikws.debug_host_plan("dw3")
+    assert len(mult) == 30 + 30 + 3 and np.all((mult >= (1 << 30)) & (mult < (1 << 31)))
+
+
 def test_float_graph_is_lowered(eikws):
     fb, mult, _ = eikws.debug_host_plan("l476f32")  # BASELINE config 5: float32 twin, no requantisation tables
     assert fb.shape == (129, 32) and len(mult) == 0

@@ -8,7 +8,7 @@ import pytest
 from oracle_lib import PortOracle, RefOracle, have_ref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODELS = ("l476", "l432", "gsc12", "l476f32", "zip6")
+MODELS = ("l476", "l432", "gsc12", "l476f32", "zip6", "dw3")
 INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}
 
 
@@ -108,7 +108,7 @@ def test_oversized_signal_is_a_dsp_error(synth):
     assert rc == -5
 
 
-@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12") and have_ref("l476f32") and have_ref("zip6")), reason="reference build (oracle/_ref) not present")
+@pytest.mark.skipif(not (have_ref("l476") and have_ref("l432") and have_ref("gsc12") and have_ref("l476f32") and have_ref("zip6") and have_ref("dw3")), reason="reference build (oracle/_ref) not present")
 @pytest.mark.parametrize("name", MODELS)
 def test_port_matches_reference_live(name, synth):
     ref, port = RefOracle(name), PortOracle(name)

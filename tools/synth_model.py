@@ -9,6 +9,9 @@ very same Register_*/trained_model_init boundary as a real Edge Impulse export.
     python tools/synth_model.py <L432 export root> <out dir>
     python tools/synth_model.py --float <L432 export root (template)> <L476 export root (weights)> <out dir>
       -> BASELINE config 5: float32 twin of the L476 model (weights dequantised, all tensors kTfLiteFloat32)
+    python tools/synth_model.py --depthwise <L432 export root> <out dir>
+      -> the L432 graph with its second convolution replaced by DEPTHWISE_CONV_2D (depth multiplier 1, 30 channels, k7):
+         the operator the north star names but no shipped graph uses
 
 Nothing from the reference is stored in this repo: its generated files are read as TEMPLATES at generation time and
 only the data tables are substituted (regex), the result is written under the (git-ignored) output directory:
@@ -159,6 +162,73 @@ def main_float(template_root, weights_root, out_root):
     print("synthesised float32 twin under", out_root, "arena", off + 8192)
 
 
+def main_depthwise(src_root, out_root):
+    """conv k7 13->30, ADD+ReLU, pool 7, DEPTHWISE conv k7 (30 channels, multiplier 1), ADD+ReLU, pool 7, FC 30->3, softmax"""
+    rng = np.random.default_rng(SEED + 1)
+    cpp = open(os.path.join(src_root, "tflite-model", "trained_model_compiled.cpp")).read()
+    hdr = open(os.path.join(src_root, "tflite-model", "trained_model_compiled.h")).read()
+    meta = open(os.path.join(src_root, "model-parameters", "model_metadata.h")).read()
+    blocks = open(os.path.join(src_root, "model-parameters", "dsp_blocks.h")).read()
+    n_labels = int(re.search(r"#define EI_CLASSIFIER_LABEL_COUNT\s+(\d+)", meta).group(1))
+    C2 = 30  # channels through the second block
+
+    def weights(count):
+        return np.clip(np.round(rng.normal(0, 35, count)), -127, 127).astype(np.int64)
+
+    # operator table: one more registration, node 7 switches to it
+    cpp = sub_one(r"OP_SOFTMAX,\s+OP_LAST", "OP_SOFTMAX, OP_DEPTHWISE_CONV_2D,  OP_LAST", cpp)
+    cpp = sub_one(r"(registrations\[OP_CONV_2D\] = \*tflite::ops::micro::Register_CONV_2D\(\);)",
+                  "registrations[OP_CONV_2D] = *tflite::ops::micro::Register_CONV_2D();\n"
+                  "  registrations[OP_DEPTHWISE_CONV_2D] = *tflite::ops::micro::Register_DEPTHWISE_CONV_2D();", cpp)
+    cpp = sub_one(r"const TfLiteConvParams opdata7 = \{[^;]*\};", "const TfLiteDepthwiseConvParams opdata7 = { kTfLitePaddingSame, 1,1, 1, kTfLiteActNone, 1,1 };", cpp)
+    cpp = sub_one(r"(&opdata7\)\), )OP_CONV_2D", "&opdata7)), OP_DEPTHWISE_CONV_2D", cpp)
+    # depthwise filter [1, 1, 7, C2], per-channel scales along dimension 3; bias int32[C2]
+    cpp = set_data(cpp, 9, "int8_t", f"1*1*7*{C2}", weights(7 * C2))
+    cpp = set_dims(cpp, 9, [1, 1, 7, C2])
+    w_s = (np.exp(rng.uniform(np.log(0.01), np.log(0.03), C2))).astype(np.float32).astype(np.float64)
+    cpp = set_scales(cpp, 9, w_s)
+    cpp = sub_one(r"(const TfLiteAffineQuantization quant9 = \{ \(TfLiteFloatArray\*\)&quant9_scale, \(TfLiteIntArray\*\)&quant9_zero, )0( \};)",
+                  "const TfLiteAffineQuantization quant9 = { (TfLiteFloatArray*)&quant9_scale, (TfLiteIntArray*)&quant9_zero, 3 };", cpp)
+    cpp = set_data(cpp, 8, "int32_t", str(C2), rng.integers(-300, 301, C2))
+    cpp = set_dims(cpp, 8, [C2])
+    cpp = set_scales(cpp, 8, (w_s * get_scales(cpp, 22)[0]).astype(np.float32).astype(np.float64))
+    cpp = set_tensor_bytes(cpp, "tensor_data8", 4 * C2)
+    cpp = set_tensor_bytes(cpp, "tensor_data9", 7 * C2)
+    # ADD constant of block 2 and the fully connected layer follow the channel count
+    cpp = set_data(cpp, 3, "int8_t", str(C2), rng.integers(-127, 128, C2))
+    cpp = set_dims(cpp, 3, [C2])
+    cpp = set_tensor_bytes(cpp, "tensor_data3", C2)
+    cpp = set_data(cpp, 5, "int8_t", f"{n_labels}*{C2}", weights(n_labels * C2))
+    cpp = set_dims(cpp, 5, [n_labels, C2])
+    cpp = set_tensor_bytes(cpp, "tensor_data5", n_labels * C2)
+    cpp = sub_one(r"const ALIGN\(8\) int32_t tensor_data14\[3\] = \{[^;]*\};", f"const ALIGN(8) int32_t tensor_data14[3] = {{ 1, 7, {C2}, }};", cpp)
+    cpp = sub_one(r"const ALIGN\(8\) int32_t tensor_data15\[4\] = \{[^;]*\};", f"const ALIGN(8) int32_t tensor_data15[4] = {{ 1, 7, 1, {C2}, }};", cpp)
+    for idx, dims in ((23, [1, 1, 7, C2]), (24, [1, 7, C2]), (25, [1, 7, C2]), (26, [1, 7, 1, C2]), (27, [1, 1, 1, C2]), (28, [1, C2])):
+        cpp = set_dims(cpp, idx, dims)
+    # arena: re-plan every activation tensor sequentially (no aliasing), 16-byte aligned, sizes from the dimensions
+    elems = {}
+    for m in re.finditer(r"const TfArray<(\d+), int> tensor_dimension(\d+) = \{ \d+, \{ ([^}]*)\} \};", cpp):
+        elems[int(m.group(2))] = int(np.prod([int(v) for v in m.group(3).split(",")]))
+    off = 0
+
+    def row(m):
+        nonlocal off
+        dim = int(m.group(2))
+        place = f"tensor_arena + {off}"
+        off += (elems[dim] + 15) // 16 * 16
+        return f"{{ kTfLiteArenaRw, kTfLiteInt8, {place}, (TfLiteIntArray*)&tensor_dimension{dim}, {elems[dim]},"
+
+    cpp, n = re.subn(r"\{ kTfLiteArenaRw, kTfLiteInt8, (tensor_arena \+ \d+), \(TfLiteIntArray\*\)&tensor_dimension(\d+), \d+,", row, cpp)
+    assert n == 16, n
+    cpp = sub_one(r"constexpr int kTensorArenaSize = \d+;", f"constexpr int kTensorArenaSize = {off + 8192};", cpp)
+    for sub, name, text in (("tflite-model", "trained_model_compiled.cpp", cpp), ("tflite-model", "trained_model_compiled.h", hdr),
+                            ("model-parameters", "model_metadata.h", meta), ("model-parameters", "dsp_blocks.h", blocks)):
+        os.makedirs(os.path.join(out_root, sub), exist_ok=True)
+        with open(os.path.join(out_root, sub, name), "w") as f:
+            f.write(text)
+    print("synthesised depthwise variant under", out_root, "arena", off + 8192)
+
+
 def main(src_root, out_root):
     rng = np.random.default_rng(SEED)
     n = len(LABELS)
@@ -206,6 +276,8 @@ def main(src_root, out_root):
 if __name__ == "__main__":
     if len(sys.argv) == 5 and sys.argv[1] == "--float":  # --float <template export (L432 style)> <weights export> <out>
         main_float(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif len(sys.argv) == 4 and sys.argv[1] == "--depthwise":
+        main_depthwise(sys.argv[2], sys.argv[3])
     elif len(sys.argv) == 3:
         main(sys.argv[1], sys.argv[2])
     else:
