@@ -135,6 +135,28 @@ def test_device_path_equals_host_path_and_synth_twin(impulses, synth):
     assert torch.equal(d_probs, d_probs2)  # fused == MFCC kernel + inference kernel
 
 
+@pytest.mark.parametrize("name", ["l476", "zip6", "l476f32"])
+def test_ragged_batch_sizes(name, impulses):
+    """batches that do not fill the persistent grid or the clip groups of a CTA: 1, 2, 3 clips (one group idle), odd sizes
+    around one full wave (148 SMs x 4 groups = 592), sizes that leave the last CTA half empty"""
+    import torch
+    imp = impulses[name]
+    d = imp.synth_clips_device(1300, first_clip=77, seed=0xE1D5)
+    full = imp.run_classifier_device(d).clone()
+    torch.cuda.synchronize()
+    port = PortOracle(name)
+    idx = [0, 1, 2, 590, 591, 592, 593, 1183, 1184, 1185, 1299]
+    want = port.run_classifier_i16(d[idx].cpu().numpy())
+    got = full[idx].cpu().numpy()
+    assert np.array_equal(got, want) if name not in FLOAT_MODELS else np.max(np.abs(got - want)) <= PROB_TOL_F32
+    for n in (1, 2, 3, 5, 591, 592, 593, 1183, 1185):
+        out = imp.run_classifier_device(d[:n].contiguous())
+        assert torch.equal(out, full[:n]), f"n={n}"
+        off = 1300 - n  # the same clips at another position of another batch
+        out = imp.run_classifier_device(d[off:].contiguous())
+        assert torch.equal(out, full[off:]), f"tail n={n}"
+
+
 def test_batch_properties_at_full_size(impulses, synth):
     """BASELINE config 2 size (65,536 clips): size-independent properties -- permutation/sharding invariance
     (a clip's result does not depend on its position or on its neighbours), duplicates agree, probabilities are
