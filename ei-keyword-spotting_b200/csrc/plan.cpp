@@ -830,6 +830,14 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             st.pool_act_min = s2 == 1 ? -128 : pl.act_min;
             st.pool_act_max = s2 == 1 ? 127 : pl.act_max;
             st.in_rows = cv.in_w + cv.kw - 1;
+            // the fused stage pools the ACCUMULATORS (max commutes with monotone steps): needs non-negative multipliers
+            // and a non-decreasing ADD+activation table for every channel
+            for (int oc = 0; ok && oc < cv.out_c; oc++) {
+                ok = cs->mult[oc] >= 0;
+                for (int i = 1; ok && i < 256; i++)
+                    ok = static_cast<int8_t>((*lut)[static_cast<size_t>(oc) * 256 + i]) >= static_cast<int8_t>((*lut)[static_cast<size_t>(oc) * 256 + i - 1]);
+            }
+            if (!ok) break;
             std::vector<int32_t> packed(static_cast<size_t>(cv.out_c) * cv.kw * (cp / 4), 0), bias(cv.out_c);
             for (int oc = 0; oc < cv.out_c; oc++) {
                 int32_t wsum = 0;

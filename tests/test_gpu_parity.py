@@ -155,6 +155,11 @@ def test_ragged_batch_sizes(name, impulses):
         off = 1300 - n  # the same clips at another position of another batch
         out = imp.run_classifier_device(d[off:].contiguous())
         assert torch.equal(out, full[off:]), f"tail n={n}"
+    if name == "l476":  # host-buffer entry point: 8192-clip chunks on two streams, the last chunk odd-sized
+        big = imp.synth_clips_device(8192 + 593, first_clip=77, seed=0xE1D5)
+        want = imp.run_classifier_device(big).cpu().numpy()
+        assert np.array_equal(imp.run_classifier(big.cpu().numpy()), want)
+        assert np.array_equal(want[:1300], full.cpu().numpy())
 
 
 def test_batch_properties_at_full_size(impulses, synth):
