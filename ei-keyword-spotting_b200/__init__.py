@@ -64,6 +64,11 @@ def load_library() -> C.CDLL:
     L.eikws_classify_i16_host.argtypes = [vp, vp, sz, vp]
     L.eikws_classify_f32_host.argtypes = [vp, vp, sz, vp]
     L.eikws_features_i16_host.argtypes = [vp, vp, sz, vp, vp]
+    for _fn in (L.eikws_mfe_i16_device, L.eikws_mfe_f32_device):
+        _fn.argtypes = [vp, vp, sz, vp, vp]
+    for _fn in (L.eikws_mfe_i16_host, L.eikws_mfe_f32_host):
+        _fn.argtypes = [vp, vp, sz, vp]
+    L.eikws_mfe_feature_count.argtypes = [vp]
     L.eikws_features_f32_host.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_infer_host.argtypes = [vp, vp, sz, vp]
     L.eikws_classify_taps_i16_host.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -166,6 +171,16 @@ class Impulse:
         _check(fn(self._h, _np_ptr(clips), n, _np_ptr(feat), _np_ptr(q) if quantized else None))
         return (feat, q) if quantized else feat
 
+    def extract_mfe_features(self, clips: np.ndarray) -> np.ndarray:
+        """the sibling MFE DSP block (extract_mfe_features, L432 SDK copy) with the MFCC block's geometry: [n][49 * 32]"""
+        clips = np.ascontiguousarray(clips).reshape(-1, self.raw_sample_count)
+        if clips.dtype not in (np.int16, np.float32):
+            raise TypeError("clips must be int16 or float32")
+        feat = np.empty((clips.shape[0], self._lib.eikws_mfe_feature_count(self._h)), np.float32)
+        fn = self._lib.eikws_mfe_i16_host if clips.dtype == np.int16 else self._lib.eikws_mfe_f32_host
+        _check(fn(self._h, _np_ptr(clips), clips.shape[0], _np_ptr(feat)))
+        return feat
+
     def run_inference(self, features: np.ndarray) -> np.ndarray:
         features = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, self.feature_count)
         out = np.empty((features.shape[0], self.label_count), np.float32)
@@ -199,6 +214,17 @@ class Impulse:
         _check(fn(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(features.data_ptr()) if features is not None else None,
                   C.c_void_p(qfeatures.data_ptr()) if qfeatures is not None else None, stream))
         return features if qfeatures is None else (features, qfeatures)
+
+    def extract_mfe_features_device(self, clips, features=None):
+        import torch
+        assert clips.is_cuda and clips.is_contiguous() and clips.device.index == self.device
+        n = clips.numel() // self.raw_sample_count
+        if features is None:
+            features = torch.empty((n, self._lib.eikws_mfe_feature_count(self._h)), dtype=torch.float32, device=clips.device)
+        stream = C.c_void_p(torch.cuda.current_stream(clips.device).cuda_stream)
+        fn = self._lib.eikws_mfe_i16_device if clips.dtype == torch.int16 else self._lib.eikws_mfe_f32_device
+        _check(fn(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(features.data_ptr()), stream))
+        return features
 
     def run_inference_device(self, features, out=None):
         import torch

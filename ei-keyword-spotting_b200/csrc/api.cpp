@@ -367,6 +367,84 @@ int eikws_classify_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, 
     return host_run(h, pcm, static_cast<size_t>(kSamples) * 2, false, nullptr, n, true, probs, features, qfeatures);
 }
 
+// ---- the sibling MFE DSP block (extract_mfe_features of the reference's newer SDK copy, L432 ei_run_dsp.h:369-418) ---------
+// Geometry = the impulse's MFCC block (frame length/stride, filters, FFT, band, window); features [n][49 * 32].
+int eikws_mfe_feature_count(const eikws_handle *h) { return h ? kFrames * kFilters : 0; }
+
+static int launch_mfe_on(eikws_handle *h, const void *d_clips, bool f32, size_t n, float *d_out, cudaStream_t st) {
+    if (n == 0) return EIKWS_OK;
+    if (reinterpret_cast<uintptr_t>(d_clips) & 15) return fail(EIKWS_ERR_BAD_ARG, "clip buffer must be 16-byte aligned (TMA bulk copy)");
+    MfeArgs a;
+    a.plan = h->dev.d_plan;
+    a.clips = d_clips;
+    a.input_is_f32 = f32;
+    a.n_clips = n;
+    a.out = d_out;
+    a.grid = grid_for(h, n);
+    a.stream = st;
+    cudaError_t e = launch_mfe(a);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    h->launches++;
+    return EIKWS_OK;
+}
+int eikws_mfe_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n, float *d_features, void *stream) {
+    if (!h || !d_pcm || !d_features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch_mfe_on(h, d_pcm, false, n, d_features, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+}
+int eikws_mfe_f32_device(eikws_handle *h, const float *d_samples, size_t n, float *d_features, void *stream) {
+    if (!h || !d_samples || !d_features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    DeviceGuard guard(h->device);
+    return launch_mfe_on(h, d_samples, true, n, d_features, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+}
+static int mfe_host(eikws_handle *h, const void *in, size_t bytes_per_clip, bool f32, size_t n, float *features) {
+    if (n == 0) return EIKWS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const size_t F = static_cast<size_t>(kFrames) * kFilters;
+    int rc;
+    cudaError_t e;
+    if ((rc = ensure(&h->d_in, &h->d_in_bytes, n * bytes_per_clip))) return rc;
+    if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
+    if ((e = cudaMemcpyAsync(h->d_in, in, n * bytes_per_clip, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return cuda_fail(e, "H2D clips");
+    if ((rc = launch_mfe_on(h, h->d_in, f32, n, h->d_feat, h->stream))) return rc;
+    if ((e = cudaMemcpyAsync(features, h->d_feat, n * F * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return cuda_fail(e, "D2H features");
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
+    return EIKWS_OK;
+}
+int eikws_mfe_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *features) {
+    if (!h || !pcm || !features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return mfe_host(h, pcm, static_cast<size_t>(kSamples) * 2, false, n, features);
+}
+int eikws_mfe_f32_host(eikws_handle *h, const float *samples, size_t n, float *features) {
+    if (!h || !samples || !features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    return mfe_host(h, samples, static_cast<size_t>(kSamples) * 4, true, n, features);
+}
+// extract_mfe_features(signal_t*, matrix_t*, void *config) through the pull callback; cfg mirrors ei_dsp_config_mfe_t
+// (L432 model-parameters/model_metadata.h:103-112) and must describe the geometry the kernels are specialised for
+int eikws_extract_mfe_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, const eikws_mfe_config *cfg, float *features,
+                             size_t capacity) {
+    if (!h || !get_data || !features || !cfg) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    const MfccConfig &m = h->graph.mfcc;
+    if (cfg->axes != 1) return fail(EIKWS_ERR_DSP, "MFE block: axes must be 1 (ei_run_dsp.h:372-374)");
+    if (cfg->frame_length != m.frame_length || cfg->frame_stride != m.frame_stride || cfg->num_filters != m.num_filters ||
+        cfg->fft_length != m.fft_length || cfg->low_frequency != m.low_frequency || cfg->high_frequency != m.high_frequency ||
+        cfg->win_size != m.win_size)
+        return fail(EIKWS_ERR_UNSUPPORTED, "MFE block: only the geometry of the impulse's MFCC block is implemented");
+    if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
+    if (capacity < static_cast<size_t>(kFrames) * kFilters) return fail(EIKWS_ERR_DSP, "MFE block: output matrix too small (ei_run_dsp.h:384-388)");
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        DeviceGuard guard(h->device);
+        if (!h->h_pinned) {
+            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        }
+    }
+    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
+    return eikws_mfe_f32_host(h, h->h_pinned, 1, features);
+}
+
 // ---- single clip through the reference's pull callback -----------------------------------------------------
 // run_classifier (ei_run_classifier.h:650-714).  The reference pulls the signal in ~98 pieces
 // ((off,320) frames and (off-1,1) history samples); any call pattern is legal, so the whole clip is pulled once.

@@ -32,6 +32,18 @@ struct LaunchArgs {
 
 cudaError_t launch_run_classifier(const LaunchArgs &a);
 
+// the sibling MFE DSP block: [n_clips][49 * 32] features
+struct MfeArgs {
+    const DevPlan *plan = nullptr;
+    const void *clips = nullptr;  // device: [n_clips][16000] int16 or float32
+    bool input_is_f32 = false;
+    size_t n_clips = 0;
+    float *out = nullptr;         // device: [n_clips][49 * 32]
+    int grid = 0;
+    cudaStream_t stream = nullptr;
+};
+cudaError_t launch_mfe(const MfeArgs &a);
+
 // one slice for every stream (run_classifier_continuous); requires the fused int8 classifier plan
 struct ContinuousArgs {
     const DevPlan *plan = nullptr;

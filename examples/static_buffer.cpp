@@ -6,6 +6,7 @@
 //       -L<repo>/ei-keyword-spotting_b200 -leikws_b200 -Wl,-rpath,<repo>/ei-keyword-spotting_b200 -o static_buffer
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "edge-impulse-sdk/classifier/ei_run_classifier.h"
 
@@ -36,6 +37,24 @@ int main(int argc, char **argv) {
     signal_t signal;
     signal.total_length = EI_CLASSIFIER_RAW_SAMPLE_COUNT;
     signal.get_data = &get_signal_data;
+    if (argc > 2 && !strcmp(argv[2], "mfe")) {
+        // the sibling DSP block of the newer SDK copy, called the way generated dsp_blocks.h entries are called:
+        // extract_fn(signal, matrix, config).  No shipped impulse carries an MFE block, so its config (the layout of
+        // ei_dsp_config_mfe_t) is filled from the MFCC block's geometry.
+        const ei_dsp_config_mfcc_t *mc = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
+        eikws_mfe_config cfg = {1, mc->frame_length, mc->frame_stride, (int)mc->num_filters, (int)mc->fft_length, (int)mc->low_frequency,
+                                (int)mc->high_frequency, (int)mc->win_size};
+        static float feats[4096];
+        ei::matrix_t fm(1, 4096, feats);
+        int rc = extract_mfe_features(&signal, &fm, &cfg);
+        if (rc != 0) {
+            printf("extract_mfe_features returned %d\n", rc);
+            return 1;
+        }
+        printf("MFE features: %u x %u\n", (unsigned)fm.rows, (unsigned)fm.cols);
+        for (uint32_t i = 0; i < fm.cols; i++) printf("mfe %u %.9g\n", (unsigned)i, feats[i]);
+        return 0;
+    }
     ei_impulse_result_t result;
     EI_IMPULSE_ERROR r = run_classifier(&signal, &result, false);
     if (r != EI_IMPULSE_OK) {

@@ -142,6 +142,20 @@ static int eikws_dropin_extract_mfcc(ei::signal_t *signal, ei::matrix_t *output_
     return EIDSP_OK;
 }
 
+/* reference (L432 copy) ei_run_dsp.h:369-418; the output matrix becomes [1][frames * num_filters] (:414-415) */
+__attribute__((unused)) static int eikws_dropin_extract_mfe(ei::signal_t *signal, ei::matrix_t *output_matrix, void *config_ptr) {
+    eikws_handle *h = eikws_dropin_handle();
+    if (!h) return -1004;
+    if (!config_ptr) return EIDSP_MATRIX_SIZE_MISMATCH;
+    eikws_dropin_current_signal = signal;
+    int rc = eikws_extract_mfe_signal(h, &eikws_dropin_get_data, signal->total_length, (const eikws_mfe_config *)config_ptr,
+                                      output_matrix->buffer, (size_t)output_matrix->rows * output_matrix->cols);
+    if (rc != EIKWS_OK) return EIDSP_MATRIX_SIZE_MISMATCH;
+    output_matrix->cols = (uint32_t)eikws_mfe_feature_count(h);
+    output_matrix->rows = 1;
+    return EIDSP_OK;
+}
+
 namespace {
 
 /* continuous mode state of the (single) stream this process serves, like the reference's statics (:116-121, :187) */

@@ -17,4 +17,11 @@ __attribute__((unused)) static int extract_mfcc_features(ei::signal_t *signal, e
     return eikws_dropin_extract_mfcc(signal, output_matrix);
 }
 
+/* The sibling MFE block of the newer SDK copy (nucleo-l432-keyword-spotting/.../classifier/ei_run_dsp.h:369-418).
+ * config_ptr points at the application's ei_dsp_config_mfe_t (model-parameters/model_metadata.h:103-112 of that export);
+ * it is read through a layout twin so that exports without that type (L476) still compile. */
+__attribute__((unused)) static int extract_mfe_features(ei::signal_t *signal, ei::matrix_t *output_matrix, void *config_ptr) {
+    return eikws_dropin_extract_mfe(signal, output_matrix, config_ptr);
+}
+
 #endif /* EIKWS_EI_RUN_DSP_H_ */

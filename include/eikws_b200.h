@@ -116,6 +116,31 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
 /* extract_mfcc_features (ei_run_dsp.h:256-308) for one clip pulled through the same callback: features[feature_count] */
 int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *features);
 
+/* ---- the sibling MFE DSP block: extract_mfe_features of the reference's newer SDK copy
+ * (nucleo-l432-keyword-spotting/keyword-spotting-02-v3/edge-impulse-sdk/classifier/ei_run_dsp.h:369-418):
+ * mel filterbank energies of the raw frames (no pre-emphasis, no log), sliding-window mean subtraction, min/max scaling of
+ * the whole matrix.  The block uses the geometry of the impulse's MFCC block; features are [n][eikws_mfe_feature_count()]
+ * = [n][frames * num_filters], row-major [frame][filter] like the reference's output matrix. --- */
+int eikws_mfe_feature_count(const eikws_handle *h);
+int eikws_mfe_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n_clips, float *d_features, void *stream);
+int eikws_mfe_f32_device(eikws_handle *h, const float *d_samples, size_t n_clips, float *d_features, void *stream);
+int eikws_mfe_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *features);
+int eikws_mfe_f32_host(eikws_handle *h, const float *samples, size_t n_clips, float *features);
+/* mirrors ei_dsp_config_mfe_t (same directory, model-parameters/model_metadata.h:103-112) */
+typedef struct {
+    int axes;
+    float frame_length;
+    float frame_stride;
+    int num_filters;
+    int fft_length;
+    int low_frequency;
+    int high_frequency;
+    int win_size;
+} eikws_mfe_config;
+/* one clip pulled through the signal callback; EIKWS_ERR_UNSUPPORTED when cfg is not the MFCC block's geometry */
+int eikws_extract_mfe_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, const eikws_mfe_config *cfg,
+                             float *features, size_t capacity);
+
 /* ---- continuous mode: run_classifier_continuous (ei_run_classifier.h:184-282) over many streams --------------
  * Every call feeds ONE slice (raw_sample_count / slices_per_window samples) of every stream; all streams advance in
  * lock step.  Per stream the semantics are those of one reference process from power-up: per-slice MFCC without CMVN

@@ -39,6 +39,11 @@ int kws_oracle_mfcc_f32(const kws_mfcc_cfg *c, const float *x, int n, float *fea
 /* pcm: int16, converted exactly like numpy::int16_to_float (numpy.hpp:1289-1298) */
 int kws_oracle_mfcc_i16(const kws_mfcc_cfg *c, const int16_t *pcm, int n, float *features, kws_mfcc_taps *taps);
 
+/* the sibling MFE DSP block (extract_mfe_features of the reference's newer SDK copy) with the geometry of the MFCC block:
+ * features[frames * num_filters]; returns the feature count or a negative error */
+int kws_oracle_mfe_block_f32(const kws_mfcc_cfg *c, const float *x, int n, float *features);
+int kws_oracle_mfe_block_i16(const kws_mfcc_cfg *c, const int16_t *pcm, int n, float *features);
+
 /* ---- classifier (model container = the raw graph written by tools/ingest) ---- */
 typedef struct kws_model kws_model;
 kws_model *kws_model_load(const void *blob, size_t bytes); /* NULL on parse error */

@@ -225,6 +225,31 @@ int ref_mfcc_nocmvn_i16(const int16_t *pcm, int n, float *out, int *frames) {
 }
 
 // One frame's magnitude spectrum via numpy::rfft (numpy.hpp:1091-1156): out[n_fft/2+1]
+#ifdef REF_HAS_MFE_BLOCK
+// The sibling DSP block of the newer SDK copy (L432): extract_mfe_features (ei_run_dsp.h:369-418) = mel filterbank energies
+// (no pre-emphasis, no log), sliding-window mean subtraction, min/max scaling of the whole matrix.  The block's config
+// takes the geometry of the model's MFCC block (no shipped impulse carries an MFE block of its own).
+int ref_mfe_block_i16(const int16_t *pcm, int n, float *features, int capacity) {
+    const ei_dsp_config_mfcc_t *mc = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
+    ei_dsp_config_mfe_t cfg;
+    cfg.axes = 1;
+    cfg.frame_length = mc->frame_length;
+    cfg.frame_stride = mc->frame_stride;
+    cfg.num_filters = mc->num_filters;
+    cfg.fft_length = mc->fft_length;
+    cfg.low_frequency = mc->low_frequency;
+    cfg.high_frequency = mc->high_frequency;
+    cfg.win_size = mc->win_size;
+    g_pcm = pcm;
+    signal_t sig;
+    sig.total_length = (size_t)n;
+    sig.get_data = &get_data_i16;
+    ei::matrix_t fm(1, capacity, features);
+    int r = extract_mfe_features(&sig, &fm, &cfg);
+    return r == 0 ? (int)(fm.rows * fm.cols) : r;
+}
+#endif
+
 int ref_rfft_mag(const float *frame, int frame_len, int n_fft, float *out) {
     return ei::numpy::rfft(frame, frame_len, out, n_fft / 2 + 1, n_fft);
 }

@@ -67,6 +67,8 @@ def main():
                    features=feats, probs=probs, mel0=mel0, energy0=en0, mfcc0=mfcc0, filterbank=ref.filterbank(),
                    features_f32in=feats_f32, nn_features=F, nn_probs=nn_probs, labels=np.array(ref.labels))
         n_t = len(tens[0])
+        if ref.has_mfe_block:  # the sibling MFE DSP block exists only in the newer SDK copy (L432 build)
+            out["mfe_features"] = ref.mfe_block_i16(clips)
         intact = INTACT_BY_MODEL.get(name, INTACT)
         out["intact"] = np.array([[k, lo, hi] for k, (lo, hi) in intact.items()], np.int32)
         for k, (lo, hi) in intact.items():

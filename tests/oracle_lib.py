@@ -68,6 +68,19 @@ class RefOracle:
             assert rc == 0, rc
         return out
 
+    @property
+    def has_mfe_block(self) -> bool:
+        return hasattr(self.lib, "ref_mfe_block_i16")  # only the newer SDK copy (L432) ships extract_mfe_features
+
+    def mfe_block_i16(self, pcm: np.ndarray) -> np.ndarray:
+        """extract_mfe_features with the geometry of the model's MFCC block: [n][49 * 32]"""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, N_SAMPLES)
+        out = np.zeros((pcm.shape[0], 49 * 32), np.float32)
+        for i in range(pcm.shape[0]):
+            rc = self.lib.ref_mfe_block_i16(_p(pcm[i], C.c_int16), N_SAMPLES, _p(out[i], C.c_float), out.shape[1])
+            assert rc == out.shape[1], rc
+        return out
+
     def mfcc_f32(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, N_SAMPLES)
         out = np.zeros((x.shape[0], self.n_features), np.float32)
@@ -168,6 +181,14 @@ class PortOracle:
         self.n_tensors = L.kws_model_num_tensors(self.m)
         self.cfg = L.kws_model_mfcc_cfg(self.m)
         self.labels = [L.kws_model_label(self.m, i).decode() for i in range(self.n_labels)]
+
+    def mfe_block_i16(self, pcm: np.ndarray) -> np.ndarray:
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, N_SAMPLES)
+        out = np.zeros((pcm.shape[0], 49 * 32), np.float32)
+        for i in range(pcm.shape[0]):
+            rc = self.lib.kws_oracle_mfe_block_i16(self.cfg, _p(pcm[i], C.c_int16), N_SAMPLES, _p(out[i], C.c_float))
+            assert rc == out.shape[1], rc
+        return out
 
     def mfcc_i16(self, pcm: np.ndarray, taps=False):
         pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, N_SAMPLES)

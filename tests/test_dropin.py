@@ -49,6 +49,21 @@ def test_dropin_run_classifier_matches_oracle(tag, tmp_path, synth):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", ["l476", "l432"])
+def test_dropin_extract_mfe_features_matches_oracle(tag, tmp_path, synth):
+    """the sibling MFE DSP block through the drop-in ei_run_dsp.h entry point (extract_fn(signal, matrix, config))"""
+    clip = synth.synth_clips(1, first_clip=78)[0]
+    f = tmp_path / "clip.pcm"
+    clip.tofile(f)
+    r = subprocess.run([_binary(tag), str(f), "mfe"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MFE features: 1 x 1568" in r.stdout
+    got = np.array([float(v) for v in re.findall(r"^mfe \d+ (\S+)$", r.stdout, flags=re.M)], np.float32)
+    want = PortOracle(tag).mfe_block_i16(clip)[0]
+    assert np.array_equal(got, want)  # %.9g round-trips a float32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["l476", "l432"])
 def test_dropin_run_classifier_continuous_matches_oracle(tag, tmp_path, synth):
     """the firmware main loop (signal_t + run_classifier_continuous per 250 ms slice) against the drop-in header"""
     from oracle_lib import PortStream

@@ -135,6 +135,26 @@ def test_device_path_equals_host_path_and_synth_twin(impulses, synth):
     assert torch.equal(d_probs, d_probs2)  # fused == MFCC kernel + inference kernel
 
 
+def test_mfe_block_matches_reference(impulses, synth):
+    """the sibling MFE DSP block (extract_mfe_features, newer SDK copy): bit-identical to the unmodified reference (golden,
+    L432 band) and to the C oracle on fresh clips for both bands (L476: 300-4000 Hz, L432: 300-8000 Hz); int16, float32 and
+    device entry points; NaN rows of degenerate clips (max == min) included"""
+    import torch
+    g = golden("l432")
+    clips = golden_clips(synth, g)
+    got = impulses["l432"].extract_mfe_features(clips)
+    assert same_floats(got, g["mfe_features"])
+    fresh = synth.synth_clips(300, first_clip=9000, seed=0xFEED)
+    for name in ("l476", "l432"):
+        imp = impulses[name]
+        want = PortOracle(name).mfe_block_i16(fresh)
+        assert same_floats(imp.extract_mfe_features(fresh), want)
+        xf = fresh.astype(np.float32) / np.float32(32768)
+        assert same_floats(imp.extract_mfe_features(xf), want)
+        d = torch.from_numpy(fresh).to("cuda:0")
+        assert same_floats(imp.extract_mfe_features_device(d).cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("name", ["l476", "zip6", "l476f32"])
 def test_ragged_batch_sizes(name, impulses):
     """batches that do not fill the persistent grid or the clip groups of a CTA: 1, 2, 3 clips (one group idle), odd sizes

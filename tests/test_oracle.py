@@ -77,6 +77,18 @@ def test_port_matches_golden_int8_classifier(name):
     assert np.array_equal(np.stack([t[nt - 1] for t in tens]), g["nn_t_out"])
 
 
+def test_mfe_block_port_matches_golden(synth):
+    """extract_mfe_features of the newer SDK copy (L432 ei_run_dsp.h:369-418): the golden comes from the unmodified reference;
+    degenerate clips (silence, DC) have max == min and turn into NaN rows in both (0 * inf)"""
+    g = golden("l432")
+    got = PortOracle("l432").mfe_block_i16(golden_clips(synth, g))
+    want = g["mfe_features"]
+    assert got.shape == want.shape == (len(want), 49 * 32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    finite = np.isfinite(want).all(axis=1)
+    assert finite.sum() >= 40 and np.all(want[finite].min(axis=1) == 0.0) and np.all(np.abs(want[finite].max(axis=1) - 1.0) < 1e-6)
+
+
 def test_silence_hits_epsilon_paths(synth):
     """all-zero clip: every power bin is 0 -> energy and mel are replaced by FLT_EPSILON (feature.hpp:295-297,
     functions.hpp:63-69).  All frames are identical, yet c0's window mean (sum of 101 equal floats / 101) is not exactly

@@ -1,0 +1,30 @@
+"""Throughput of every (model, input sample type) combination on one GPU: python tools/combo_sweep.py [n_clips]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import eikws_pkg
+
+m = eikws_pkg.load()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+for name in ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32"):
+    imp = m.Impulse(name)
+    pcm = imp.synth_clips_device(n)
+    for dtype in ("int16", "float32"):
+        clips = pcm if dtype == "int16" else (pcm.to(torch.float32) / 32768.0).contiguous()
+        out = torch.empty((n, imp.label_count), dtype=torch.float32, device="cuda:0")
+        for _ in range(2):
+            imp.run_classifier_device(clips, out=out)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            imp.run_classifier_device(clips, out=out)
+        b.record()
+        torch.cuda.synchronize()
+        print(f"{name:8s} {dtype:8s} {n * 5 / (a.elapsed_time(b) * 1e-3) / 1e6:7.3f} M clips/s", flush=True)
+        del clips
+    del pcm
