@@ -390,12 +390,12 @@ static int launch_mfe_on(eikws_handle *h, const void *d_clips, bool f32, size_t 
 int eikws_mfe_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n, float *d_features, void *stream) {
     if (!h || !d_pcm || !d_features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
     DeviceGuard guard(h->device);
-    return launch_mfe_on(h, d_pcm, false, n, d_features, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+    return launch_mfe_on(h, d_pcm, false, n, d_features, static_cast<cudaStream_t>(stream));
 }
 int eikws_mfe_f32_device(eikws_handle *h, const float *d_samples, size_t n, float *d_features, void *stream) {
     if (!h || !d_samples || !d_features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
     DeviceGuard guard(h->device);
-    return launch_mfe_on(h, d_samples, true, n, d_features, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+    return launch_mfe_on(h, d_samples, true, n, d_features, static_cast<cudaStream_t>(stream));
 }
 static int mfe_host(eikws_handle *h, const void *in, size_t bytes_per_clip, bool f32, size_t n, float *features) {
     if (n == 0) return EIKWS_OK;

@@ -28,3 +28,19 @@ for name in ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32"):
         print(f"{name:8s} {dtype:8s} {n * 5 / (a.elapsed_time(b) * 1e-3) / 1e6:7.3f} M clips/s", flush=True)
         del clips
     del pcm
+
+# the sibling MFE DSP block (features only: 32,000 B in, 6,272 B out per clip)
+imp = m.Impulse("l432")
+pcm = imp.synth_clips_device(n)
+feat = imp.extract_mfe_features_device(pcm)
+for _ in range(2):
+    imp.extract_mfe_features_device(pcm, features=feat)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    imp.extract_mfe_features_device(pcm, features=feat)
+b.record()
+torch.cuda.synchronize()
+thr = n * 5 / (a.elapsed_time(b) * 1e-3)
+print(f"MFE block int16 {thr / 1e6:7.3f} M clips/s = {thr * (32000 + 6272) / 1e9:6.1f} GB/s algorithmic", flush=True)
