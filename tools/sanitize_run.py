@@ -1,0 +1,44 @@
+"""Touch every kernel variant once with small batches -- the command compute-sanitizer is pointed at:
+   compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_run.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import eikws_pkg
+
+m = eikws_pkg.load()
+synth = sys.modules["eikws_b200.synth"] if "eikws_b200.synth" in sys.modules else __import__("eikws_b200.synth", fromlist=["x"])
+n = 613  # odd, a little more than one wave of clip groups
+clips = synth.synth_clips(n, first_clip=5)
+d16 = torch.from_numpy(clips).to("cuda:0")
+d32 = (d16.to(torch.float32) / 32768.0).contiguous()
+for name in ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32"):
+    imp = m.Impulse(name)
+    p16 = imp.run_classifier_device(d16)
+    p32 = imp.run_classifier_device(d32)
+    feats = imp.extract_mfcc_features_device(d16)
+    pinf = imp.run_inference_device(feats)
+    torch.cuda.synchronize()
+    assert torch.equal(p16, p32) and torch.equal(p16, pinf), name
+    mfe = imp.extract_mfe_features_device(d16)
+    mfe32 = imp.extract_mfe_features_device(d32)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(mfe), torch.nan_to_num(mfe32))
+    host = imp.run_classifier(clips[:40])
+    assert np.array_equal(host, p16[:40].cpu().numpy())
+    if name in ("l476", "l432", "gsc12", "dw3"):
+        st = m.Streams(imp, 7)
+        audio = clips[:14].reshape(7, -1)
+        for s in range(8):
+            st.push(audio[:, s * st.slice_size:(s + 1) * st.slice_size])
+        st.close()
+    imp.close()
+imp = m.Impulse("l476")
+i2s = torch.randint(-2 ** 31, 2 ** 31 - 1, (4 * 16000 * 3,), dtype=torch.int32, device="cuda:0")
+imp.decimate_i2s_device(i2s, 16000 * 3)
+torch.cuda.synchronize()
+print("all kernel variants ran")
