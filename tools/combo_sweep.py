@@ -29,6 +29,22 @@ for name in ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32"):
         del clips
     del pcm
 
+# MFCC DSP block alone (extract_mfcc_features): 32,000 B in, 2,548 B out per clip
+imp = m.Impulse("l476")
+pcm = imp.synth_clips_device(n)
+feat = imp.extract_mfcc_features_device(pcm)
+for _ in range(2):
+    imp.extract_mfcc_features_device(pcm, features=feat)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    imp.extract_mfcc_features_device(pcm, features=feat)
+b.record()
+torch.cuda.synchronize()
+print(f"MFCC block int16 {n * 5 / (a.elapsed_time(b) * 1e-3) / 1e6:7.3f} M clips/s", flush=True)
+del pcm, feat
+
 # the sibling MFE DSP block (features only: 32,000 B in, 6,272 B out per clip)
 imp = m.Impulse("l432")
 pcm = imp.synth_clips_device(n)
