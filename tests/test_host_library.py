@@ -115,3 +115,14 @@ def test_wav_ingest_roundtrip(eikws, synth, tmp_path):
         w.writeframes(b"\0" * 400)
     with pytest.raises(ValueError):
         ingest.read_wav(bad)
+
+
+def test_cmvn_rounding_trick_equals_the_float_cast(tmp_path):
+    """the kernel's two-FMA rounding of the CMVN variance sum (csrc/kernels.cu, cmvn_chains) against the reference's
+    (float)(double) cast (numpy.hpp:819-825): tools/check_round_trick.c, millions of operands incl. exact ties and denormals"""
+    import subprocess
+    exe = str(tmp_path / "check_round_trick")
+    subprocess.run(["gcc", "-O2", "-march=native", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tools", "check_round_trick.c"), "-lm"], check=True)
+    out = subprocess.run([exe, "30000000"], check=True, capture_output=True, text=True).stdout
+    m = re.search(r"checked=(\d+) mismatches=(\d+) exact_ties=(\d+) float_denormal_sums=(\d+)", out)
+    assert m and int(m.group(2)) == 0 and int(m.group(1)) > 10_000_000 and int(m.group(3)) > 100_000 and int(m.group(4)) > 10_000, out
