@@ -53,6 +53,7 @@ def load_library() -> C.CDLL:
     L.eikws_set_ctas_per_sm.argtypes = [vp, i32]
     L.eikws_set_clips_per_cta.argtypes = [vp, i32]
     L.eikws_set_skew_ns.argtypes = [vp, i32]
+    L.eikws_set_tensor_core.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -133,6 +134,10 @@ class Impulse:
 
     def set_ctas_per_sm(self, n: int):
         _check(self._lib.eikws_set_ctas_per_sm(self._h, n))
+
+    def set_tensor_core(self, on: bool):
+        """block 1 of the fused int8 classifier as a tcgen05 UMMA (int16 clips, two clip groups per CTA)"""
+        _check(self._lib.eikws_set_tensor_core(self._h, 1 if on else 0))
 
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))

@@ -99,6 +99,11 @@ struct NnFusedDev {
     int32_t fc_in_off, fc_d, fc_o, fc_in_zp, fc_out_zp, fc_act_min, fc_act_max, fc_mult, fc_shift;
     int32_t tail_pool, tail_pool_act_min, tail_pool_act_max;  // stage 1 leaves its max-pool (over tail_pool positions) to the tail
     int32_t tail_off;        // scratch for the fc output / softmax output bytes
+    // tensor-core lowering of block 1 (tcgen05.mma.kind::i8, see kernels.cu): the stage-0 filter as the A operand of a
+    // 128 x N x 32 UMMA, K-major without swizzle: [8 K-chunks of 16 B = one tap][64 rows][16 B]; rows 0..out_c-1 and
+    // 32..32+out_c-1 both hold the output channels (two TMEM sub-partitions can then read every channel), tap 7 is zero
+    int32_t tc_enabled;
+    const int8_t *tc_w;      // [8][64][16]
     const int8_t *fc_w;      // [fc_o][fc_d]
     const int32_t *fc_bias;  // [fc_o] bias + in_offset * sum(weights)
     const int32_t *exp_lut;  // [256]

@@ -896,6 +896,20 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 b.bind(fu.fc_bias, b.push(fbias.data(), fbias.size() * 4));
                 b.bind(fu.exp_lut, b.push(exp_lut_src.data(), exp_lut_src.size() * 4));
                 fu.enabled = 1;
+                // A operand of the tensor-core block 1 (dev_plan.h): needs the shipped stage-0 shape (7 taps of one 16-byte row)
+                if (s0.kw == 7 && s0.cp == 16 && s0.out_c <= 30 && s0.in_w == kFrames && s0.pool == 7 && s0.pool_out == 7 && s0.pad_w == 3) {
+                    const ConvSrc *c0 = find_conv(0);
+                    std::vector<int8_t> tcw(8 * 64 * 16, 0);
+                    for (int oc = 0; oc < s0.out_c; oc++)
+                        for (int kx = 0; kx < s0.kw; kx++)
+                            for (int c2 = 0; c2 < s0.in_c; c2++) {
+                                const int8_t wv = c0->w[(oc * s0.kw + kx) * s0.in_c + c2];
+                                tcw[(static_cast<size_t>(kx) * 64 + oc) * 16 + c2] = wv;
+                                tcw[(static_cast<size_t>(kx) * 64 + 32 + oc) * 16 + c2] = wv;
+                            }
+                    b.bind(fu.tc_w, b.push(tcw.data(), tcw.size()));
+                    fu.tc_enabled = 1;
+                }
                 if (arena > hp.nn_smem_bytes) hp.nn_smem_bytes = arena;
             }
         }

@@ -274,3 +274,33 @@ def test_i2s_decimation_matches_firmware_isr(impulses):
         want = (i2s[: 4 * n_out : 4] >> 8).to(torch.int16)
         torch.cuda.synchronize()
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3"])
+def test_tensor_core_block1_is_bit_identical(name, impulses, synth):
+    """block 1 of the fused int8 classifier as a tcgen05.mma.kind::i8 over the in-place sliding windows of the quantised
+    feature matrix (kernels.cu, use_tc): integer sums, so the outputs must equal the dp4a path's and the C oracle's byte for
+    byte -- goldens (incl. the saturating / wrapping edge-case clips), fresh clips, ragged batch sizes (a clip group idle)"""
+    import torch
+    imp = impulses[name]
+    g = golden(name)
+    clips = golden_clips(synth, g)
+    d = imp.synth_clips_device(1300, first_clip=4242, seed=0xBEEF)
+    try:
+        imp.set_tensor_core(False)
+        base = imp.run_classifier_device(d).clone()
+        imp.set_tensor_core(True)
+        before = imp.launch_count
+        assert np.array_equal(imp.run_classifier(clips), g["probs"])
+        tc = imp.run_classifier_device(d).clone()
+        assert torch.equal(tc, base)
+        idx = [0, 1, 2, 591, 592, 593, 1299]
+        assert np.array_equal(tc[idx].cpu().numpy(), PortOracle(name).run_classifier_i16(d[idx].cpu().numpy()))
+        for n in (1, 2, 3, 5, 591, 593, 1185):
+            assert torch.equal(imp.run_classifier_device(d[:n].contiguous()), base[:n]), f"n={n}"
+            assert torch.equal(imp.run_classifier_device(d[1300 - n:].contiguous()), base[1300 - n:]), f"tail n={n}"
+        probs, feats, qfeats = imp.run_classifier_taps(clips)  # features / quantised features come out of the same launch
+        assert same_floats(feats, g["features"]) and np.array_equal(probs, g["probs"])
+        assert imp.launch_count > before
+    finally:
+        imp.set_tensor_core(False)
