@@ -12,6 +12,8 @@ m = eikws_pkg.load()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 imp = m.Impulse("l476")
+if os.environ.get("EIKWS_TC", "") != "":  # 0 = dp4a block 1, 1 = UMMA, 2 = UMMA + run-ahead schedule
+    imp.set_tensor_core(int(os.environ["EIKWS_TC"]))
 clips = imp.synth_clips_device(n)
 out = torch.empty((n, imp.label_count), dtype=torch.float32, device="cuda:0")
 for _ in range(reps):
