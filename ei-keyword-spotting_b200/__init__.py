@@ -54,6 +54,7 @@ def load_library() -> C.CDLL:
     L.eikws_set_clips_per_cta.argtypes = [vp, i32]
     L.eikws_set_skew_ns.argtypes = [vp, i32]
     L.eikws_set_tensor_core.argtypes = [vp, i32]
+    L.eikws_set_cmvn_shortcut.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -139,6 +140,11 @@ class Impulse:
         """block 1 of the fused int8 classifier as a tcgen05 UMMA (int16 clips, two clip groups per CTA)"""
         _check(self._lib.eikws_set_tensor_core(self._h, 1 if on else 0))
 
+    def set_cmvn_shortcut(self, on: bool):
+        """certified CMVN shortcut (default on): window statistics in one double-precision pass, rounding decision certified by
+        a rigorous error bound, uncertified chains recomputed with the reference's operation sequence -- same int8 features"""
+        _check(self._lib.eikws_set_cmvn_shortcut(self._h, 1 if on else 0))
+
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))
 
@@ -207,6 +213,20 @@ class Impulse:
         else:
             raise TypeError("clips must be int16 or float32")
         return out
+
+    def run_classifier_taps_device(self, clips, want_features=False):
+        """int16 clips on the device -> (probs, int8 quantised NN input [n,637][, float features]) from the classify kernel itself;
+        without the float features the kernel is the one run_classifier_device launches"""
+        import torch
+        assert clips.is_cuda and clips.is_contiguous() and clips.dtype == torch.int16 and clips.device.index == self.device
+        n = clips.numel() // self.raw_sample_count
+        probs = torch.empty((n, self.label_count), dtype=torch.float32, device=clips.device)
+        q = torch.empty((n, self.feature_count), dtype=torch.int8, device=clips.device)
+        feat = torch.empty((n, self.feature_count), dtype=torch.float32, device=clips.device) if want_features else None
+        stream = C.c_void_p(torch.cuda.current_stream(clips.device).cuda_stream)
+        _check(self._lib.eikws_classify_taps_i16_device(self._h, C.c_void_p(clips.data_ptr()), n, C.c_void_p(probs.data_ptr()),
+                                                        C.c_void_p(feat.data_ptr()) if want_features else None, C.c_void_p(q.data_ptr()), stream))
+        return (probs, q, feat) if want_features else (probs, q)
 
     def extract_mfcc_features_device(self, clips, features=None, qfeatures=None):
         import torch

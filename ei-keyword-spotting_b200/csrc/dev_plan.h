@@ -30,6 +30,7 @@ struct MfccDev {
     float pre_cof;
     float q_scale;  // NN input quantisation (tensor 0): q = (int8)(round(f / q_scale) + q_zp)
     int32_t q_zp;
+    float q_inv_scale;  // (float)(1 / q_scale): used only by the certified CMVN shortcut, whose bound covers its rounding
     int32_t input_is_int8;
     const float2 *tw;      // [128]  kiss_fft twiddles  (float)cos/sin(-2*pi*i/128)
     const float2 *stw;     // [64]   kiss_fftr super twiddles
@@ -39,6 +40,7 @@ struct MfccDev {
     const int32_t *fb_first;  // [32] first bin with a strictly positive weight
     const int32_t *fb_count;  // [32] number of consecutive bins with strictly positive weight
     const float *fb_w;        // [32][kFbMaxTaps]
+    int32_t fb_max_taps;      // widest filter of this model
     const uint8_t *pad_src;   // [149] source frame of every row of the symmetric-padded matrix
 };
 

@@ -19,6 +19,7 @@ struct LaunchArgs {
     bool nn_fused = false;               // the plan has a fused classifier (NnFusedDev.enabled)
     bool nn_float = false;               // float32 graph (NnDev.float_mode)
     bool nn_tc = false;                  // block 1 of the fused classifier on the tensor core (NnFusedDev.tc_enabled, 2 clip groups per CTA)
+    bool cmvn_certified = false;         // certified CMVN shortcut (tensor-core variant, no float feature output): see cmvn_certified()
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]

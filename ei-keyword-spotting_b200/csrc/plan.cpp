@@ -4,6 +4,7 @@
 // once here with the same host arithmetic (same libm calls, same float/double mix) and uploaded.
 #include "plan.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -200,6 +201,7 @@ int build_float_nn(const ModelGraph &g, HostPlan &hp, Builder &b, std::string &e
         return EIKWS_ERR_SHAPES_DONT_MATCH;
     }
     mf.q_scale = 1.0f;
+    mf.q_inv_scale = 1.0f;
     mf.q_zp = 0;
     mf.input_is_int8 = 0;
     uint32_t max_bytes = 0;
@@ -439,6 +441,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
 
     MfccDev &mf = hp.dev.mfcc;
     mf.pre_cof = c.pre_cof;
+    mf.fb_max_taps = *std::max_element(fb_count.begin(), fb_count.end());
     b.bind(mf.tw, b.push(tw.data(), tw.size() * sizeof(float2)));
     b.bind(mf.stw, b.push(stw.data(), stw.size() * sizeof(float2)));
     b.bind(mf.dtw, b.push(dtw.data(), dtw.size() * sizeof(float2)));
@@ -467,6 +470,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
         return EIKWS_ERR_SHAPES_DONT_MATCH;
     }
     mf.q_scale = tin.scale();
+    mf.q_inv_scale = static_cast<float>(1.0 / static_cast<double>(tin.scale()));
     mf.q_zp = tin.zero_point();
     mf.input_is_int8 = 1;
 

@@ -303,4 +303,46 @@ def test_tensor_core_block1_is_bit_identical(name, impulses, synth):
         assert same_floats(feats, g["features"]) and np.array_equal(probs, g["probs"])
         assert imp.launch_count > before
     finally:
-        imp.set_tensor_core(False)
+        imp.set_tensor_core(True)  # the default
+
+
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3"])
+def test_certified_cmvn_shortcut_is_bit_identical(name, impulses, synth):
+    """The default classify kernel decides round(f / scale) of most CMVN outputs from double-precision window statistics plus
+    a rigorous error bound and runs the reference's operation sequence only for the chains the bound cannot certify
+    (kernels.cu, cmvn_certified; derivation in DESIGN.md).  The int8 classifier input and the outputs must equal, byte for
+    byte, those of the kernel that runs every chain with the reference's sequence: goldens (incl. silence / DC / impulse
+    clips, where every chain takes the exact path), the oracle's input tensor, 65,536 fresh clips, ragged batch sizes."""
+    import torch
+    imp = impulses[name]
+    g = golden(name)
+    clips = golden_clips(synth, g)
+    port = PortOracle(name)
+    _, tens = port.run_inference(g["features"], want_tensors=True)
+    want_q = np.stack([t[0] for t in tens]).view(np.int8)
+    try:
+        imp.set_cmvn_shortcut(True)
+        d_clips = torch.from_numpy(clips).to("cuda:0")
+        probs, q = imp.run_classifier_taps_device(d_clips)
+        torch.cuda.synchronize()
+        assert np.array_equal(q.cpu().numpy(), want_q)
+        assert np.array_equal(probs.cpu().numpy(), g["probs"])
+        assert np.array_equal(imp.run_classifier(clips), g["probs"])
+        n = 65536
+        d = imp.synth_clips_device(n, first_clip=777000, seed=0x5EED)
+        p1, q1 = imp.run_classifier_taps_device(d)
+        p1b = imp.run_classifier_device(d)
+        imp.set_cmvn_shortcut(False)
+        p0, q0 = imp.run_classifier_taps_device(d)
+        torch.cuda.synchronize()
+        bad = (q1 != q0).any(dim=1).nonzero().flatten()
+        assert bad.numel() == 0, f"clips whose quantised features differ: {bad[:10].tolist()}"
+        assert torch.equal(p1, p0) and torch.equal(p1b, p0)
+        imp.set_cmvn_shortcut(True)
+        for m in (1, 2, 3, 5, 591, 593, 1185):
+            assert torch.equal(imp.run_classifier_device(d[:m].contiguous()), p0[:m]), f"n={m}"
+            assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p0[n - m:]), f"tail n={m}"
+        idx = [0, 1, 2, 3, 40000, 65535]
+        assert np.array_equal(p1[idx].cpu().numpy(), port.run_classifier_i16(d[idx].cpu().numpy()))
+    finally:
+        imp.set_cmvn_shortcut(True)
