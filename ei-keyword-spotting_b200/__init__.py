@@ -55,6 +55,7 @@ def load_library() -> C.CDLL:
     L.eikws_set_skew_ns.argtypes = [vp, i32]
     L.eikws_set_tensor_core.argtypes = [vp, i32]
     L.eikws_set_cmvn_shortcut.argtypes = [vp, i32]
+    L.eikws_set_work_claiming.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -144,6 +145,10 @@ class Impulse:
         """certified CMVN shortcut (default on): window statistics in one double-precision pass, rounding decision certified by
         a rigorous error bound, uncertified chains recomputed with the reference's operation sequence -- same int8 features"""
         _check(self._lib.eikws_set_cmvn_shortcut(self._h, 1 if on else 0))
+
+    def set_work_claiming(self, on: bool):
+        """work-claiming schedule of the shortcut kernel (frame pairs and the UMMA issue claimed from shared counters)"""
+        _check(self._lib.eikws_set_work_claiming(self._h, 1 if on else 0))
 
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))

@@ -20,6 +20,7 @@ struct LaunchArgs {
     bool nn_float = false;               // float32 graph (NnDev.float_mode)
     bool nn_tc = false;                  // block 1 of the fused classifier on the tensor core (NnFusedDev.tc_enabled, 2 clip groups per CTA)
     bool cmvn_certified = false;         // certified CMVN shortcut (tensor-core variant, no float feature output): see cmvn_certified()
+    bool work_claiming = false;          // with cmvn_certified: frame pairs and the UMMA issue are claimed dynamically (kDyn in kernels.cu)
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
     int8_t *qfeatures_out = nullptr;     // device, optional: [n_clips][637]
