@@ -150,6 +150,29 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank to the host cores NVML reports as local to its GPU BEFORE the pinned host buffers of the e2e leg are
+    allocated (pages are placed on the allocating thread's NUMA node): with 8 ranks streaming 55 GB/s each, buffers on the
+    wrong socket turn the PCIe-bound leg into an inter-socket-link-bound one.  Returns a short description for `config`."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if not use:
+            return "unchanged (no GPU-local core in the allowed set)"
+        os.sched_setaffinity(0, use)
+        return f"{len(use)} GPU-local cores (NVML affinity of GPU {idx})"
+    except Exception as e:  # plumbing only: never fail the bench over it
+        return f"unchanged ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,8 +193,10 @@ def main():
     if world != args.gpus and world != 1:
         raise SystemExit(f"--gpus {args.gpus} does not match WORLD_SIZE {world}")
     n_gpus = world
-    config = {"workload": f"BASELINE configs[1]: batch {args.clips_per_gpu} synthetic 1-s 16 kHz int16 clips per GPU, "
-                          f"L476 4-label int8 model (MFCC+CMVN+int8 CNN fused), inputs ({args.clips_per_gpu * 32000 / 1e9:.2f} GB/GPU) larger than L2",
+    which = {"l476": "BASELINE configs[1]", "gsc12": "BASELINE configs[3]", "l476f32": "BASELINE configs[4]"}.get(args.model, "extra model")
+    bytes_per_clip = N_SAMPLES * (4 if args.f32_input else 2)
+    config = {"workload": f"{which}: batch {args.clips_per_gpu} synthetic 1-s 16 kHz {'float32' if args.f32_input else 'int16'} clips per GPU, "
+                          f"model {args.model} (MFCC+CMVN+CNN fused in one kernel), inputs ({args.clips_per_gpu * bytes_per_clip / 1e9:.2f} GB/GPU) larger than L2",
               "model": {"l476": "l476_yes_no (EON-compiled int8, 4 labels)", "gsc12": "synthesised 12-label int8 model (BASELINE config 4)",
                         "l476f32": "float32 twin of l476 (BASELINE config 5)", "l432": "l432 (int8, 3 labels)",
                         "zip6": "third shipped model (Arduino zip, int8, 6 labels, generic op plan)"}[args.model],
@@ -207,6 +232,8 @@ def main():
         thr, cores, kind, sample = cpu_reference_throughput(args.cpu_clips_per_core)
         cpu = {"value": thr, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 
+    if n_gpus > 1 and not os.environ.get("EIKWS_BENCH_NO_BIND"):
+        config["host_affinity"] = bind_to_gpu_numa(local_rank)
     import torch
     import torch.distributed as dist
     import eikws_pkg
