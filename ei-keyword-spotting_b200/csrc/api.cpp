@@ -115,6 +115,7 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.clips_per_cta = h->clips_per_cta;
     a.sm_count = h->sm_count;
     a.skew_ns = (n >= static_cast<size_t>(h->sm_count) * h->ctas_per_sm * 8) ? h->skew_ns : 0;  // only worth it for long launches
+    a.pre_cof = h->host.dev.mfcc.pre_cof;
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
     a.stream = st;
     cudaError_t e = launch_run_classifier(a);

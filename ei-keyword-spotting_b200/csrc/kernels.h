@@ -29,6 +29,7 @@ struct LaunchArgs {
     int clips_per_cta = 1;               // 160-thread clip groups per CTA (1, 2 or 4): int16 + fused classifier path only
     int sm_count = 0;                    // SMs of the device (CTA j of an SM = blockIdx / sm_count)
     int skew_ns = 0;                     // start offset between co-resident CTAs (0 = none)
+    float pre_cof = 0.0f;                // MfccDev::pre_cof again, as a kernel argument (a constant-bank operand of the pre-emphasis multiply)
     int nn_smem_bytes = 0;               // activation arena + conv row scratch
     cudaStream_t stream = nullptr;
 };
