@@ -626,6 +626,7 @@ static int streams_push_device(eikws_streams *s, const void *d_slices, bool f32,
     a.window_full = s->window_full ? 1 : 0;
     a.maf_idx = s->maf_idx;
     a.maf_len = s->maf_len;
+    a.cmvn_certified = h->cmvn_shortcut != 0;
     a.probs = d_probs;
     a.sm_count = h->sm_count;
     size_t g = static_cast<size_t>(h->sm_count) * 4;

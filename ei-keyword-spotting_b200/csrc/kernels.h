@@ -60,6 +60,7 @@ struct ContinuousArgs {
     float *maf_buf = nullptr;         // device: [n_streams][labels][maf_len]
     float *maf_sum = nullptr;         // device: [n_streams][labels]
     int slice_offset = 0, window_full = 0, maf_idx = 0, maf_len = 1;
+    bool cmvn_certified = false;      // certified CMVN shortcut for the window classification (see cmvn_certified in kernels.cu)
     float *probs = nullptr;           // device: [n_streams][labels]
     int grid = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
