@@ -344,5 +344,17 @@ def test_certified_cmvn_shortcut_is_bit_identical(name, impulses, synth):
             assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p0[n - m:]), f"tail n={m}"
         idx = [0, 1, 2, 3, 40000, 65535]
         assert np.array_equal(p1[idx].cpu().numpy(), port.run_classifier_i16(d[idx].cpu().numpy()))
+        # the same shortcut on the dp4a lowering (tensor core off) and on float-input clips (the samples a demo callback delivers)
+        imp.set_tensor_core(False)
+        assert torch.equal(imp.run_classifier_device(d), p0)
+        imp.set_clips_per_cta(1)
+        assert torch.equal(imp.run_classifier_device(d[:4099].contiguous()), p0[:4099])
+        imp.set_clips_per_cta(2)
+        imp.set_tensor_core(True)
+        x = (d[:8192].to(torch.float32) / 32768.0).contiguous()
+        assert torch.equal(imp.run_classifier_device(x), p0[:8192])
+        assert np.array_equal(imp.run_classifier(clips.astype(np.float32) / np.float32(32768)), g["probs"])
     finally:
         imp.set_cmvn_shortcut(True)
+        imp.set_tensor_core(True)
+        imp.set_clips_per_cta(2)
