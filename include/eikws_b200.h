@@ -88,7 +88,12 @@ const char *eikws_label(const eikws_handle *h, int i);
 /* ---- batch hot path, DEVICE buffers (on the handle's device) ------------------------------- */
 /* run_classifier over n_clips clips of int16 PCM (the demos' signal: int16 -> x/32768,
  * numpy.hpp:1289-1298).  d_probs: [n_clips][label_count] float = result.classification[i].value.
- * stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous. */
+ * stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous.
+ * Exactness: for an int8 model the outputs are byte-identical to the reference CPU code built with
+ * -ffp-contract=off; the classify kernels may decide the int8 rounding of a CMVN output from double-precision window
+ * statistics and a proven error bound instead of running the reference's float chain, and run that chain whenever the
+ * bound cannot decide.  Float features (eikws_features_*) always come from the reference's exact
+ * operation sequence and are bit-identical. */
 int eikws_classify_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n_clips, float *d_probs, void *stream);
 /* same, float samples as a signal_t callback would deliver them */
 int eikws_classify_f32_device(eikws_handle *h, const float *d_samples, size_t n_clips, float *d_probs, void *stream);
