@@ -16,7 +16,21 @@ n = 613  # odd, a little more than one wave of clip groups
 clips = synth.synth_clips(n, first_clip=5)
 d16 = torch.from_numpy(clips).to("cuda:0")
 d32 = (d16.to(torch.float32) / 32768.0).contiguous()
-for name in ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32"):
+quick = "--quick" in sys.argv  # racecheck: the default model only, every schedule / lowering knob
+# every lowering of the fused int8 path on the default model: mode 6 (default), 5, 4, 7 (two clip groups), 7 (one), 2
+imp = m.Impulse("l476")
+want = imp.run_classifier_device(d16).clone()
+for knobs in ({"work_claiming": False}, {"cmvn_shortcut": False}, {"tensor_core": False}, {"tensor_core": False, "clips_per_cta": 1},
+              {"tensor_core": False, "cmvn_shortcut": False}):
+    imp.set_work_claiming(knobs.get("work_claiming", True))
+    imp.set_cmvn_shortcut(knobs.get("cmvn_shortcut", True))
+    imp.set_tensor_core(knobs.get("tensor_core", True))
+    imp.set_clips_per_cta(knobs.get("clips_per_cta", 2))
+    got = imp.run_classifier_device(d16)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), knobs
+imp.close()
+for name in (("l476",) if quick else ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32")):
     imp = m.Impulse(name)
     p16 = imp.run_classifier_device(d16)
     p32 = imp.run_classifier_device(d32)
