@@ -142,3 +142,90 @@ def _input_quant(name):
         else:
             lo = mid
     return np.float32(hi / 39.5), zp
+
+
+def reference_cmvn_f32(F32):
+    """numpy float32 emulation of processing::cmvnw + mean_axis0 + std_axis0 (processing.hpp:326-389, numpy.hpp:746-836) for a
+    [49][13] cepstra matrix, vectorised over the 637 chains: every chain still performs the reference's operations in order"""
+    f32, f64 = np.float32, np.float64
+    G = F32[pad_rows()]
+    rows = np.arange(49)
+    s = np.zeros((49, 13), f32)
+    for w in range(101):
+        s = (s + G[rows + w]).astype(f32)
+    mean = (s / f32(101.0)).astype(f32)
+    sd = np.zeros((49, 13), f32)
+    for w in range(101):
+        d = (G[rows + w] - mean).astype(f32).astype(f64)
+        sd = (sd.astype(f64) + d * d).astype(f32)
+    std = np.sqrt((sd / f32(101.0)).astype(f32)).astype(f32)
+    return ((F32 - mean).astype(f32) / (std + EPS).astype(f32)).astype(f32)
+
+
+def test_emulation_is_the_oracle(synth):
+    """pins reference_cmvn_f32 (used for the adversarial matrices below) to the plain-C oracle on real clips"""
+    port = PortOracle("l476")
+    clips = np.concatenate([synth.synth_clips(12, first_clip=99), np.stack(list(synth.special_clips().values()))])
+    feats, taps = port.mfcc_i16(clips, taps=True)
+    for ci in range(len(clips)):
+        got = reference_cmvn_f32(taps[ci]["mfcc"])
+        want = feats[ci].reshape(49, 13)
+        assert np.all((got == want) | (np.isnan(got) & np.isnan(want))), f"clip {ci}"
+
+
+def test_bound_on_adversarial_matrices():
+    """cepstra matrices no audio clip produces: huge mean/sigma ratios, near-constant columns, outliers, tiny and huge magnitudes,
+    exact ties.  A certified decision must always equal the emulated reference's; the bound must hold with room."""
+    rng = np.random.default_rng(20261017)
+    scale, zp = np.float32(0.046360891312360764), -11
+    inv_scale = np.float32(1.0 / float(scale))
+    src = pad_rows()
+    mats = []
+    for sigma in (1e-3, 1.0, 30.0, 1e3):
+        for ratio in (0.0, 10.0, 1e3, 1e5, -1e4):
+            mats.append((rng.standard_normal((49, 13)) * sigma + ratio * sigma).astype(np.float32))
+    for k in range(10):
+        m = (rng.standard_normal((49, 13)) * 3).astype(np.float32)
+        m[rng.integers(0, 49), :] += np.float32(10.0 ** rng.integers(1, 6))      # one outlier frame
+        mats.append(m)
+        mats.append((np.float32(7.25) + rng.standard_normal((49, 13)) * 1e-6).astype(np.float32))  # nearly constant
+        mats.append((rng.standard_normal((49, 13)) * 10.0 ** rng.integers(-20, 15)).astype(np.float32))
+        mats.append(np.where(rng.random((49, 13)) < 0.5, np.float32(1.0), np.float32(-1.0)).astype(np.float32) * np.float32(2.5))
+        mats.append(np.round(rng.standard_normal((49, 13)) * 4).astype(np.float32) * scale)  # many exact-looking values
+    mats.append(np.zeros((49, 13), np.float32))
+    mats.append(np.full((49, 13), 3.0, np.float32))
+    worst, certified, total = 0.0, 0, 0
+    for mi, F32 in enumerate(mats):
+        f_ref = reference_cmvn_f32(F32)
+        with np.errstate(all="ignore"):
+            t_ref = (f_ref / scale).astype(np.float32)
+            k_ref = np.where(t_ref >= 0, np.floor(t_ref.astype(np.float64) + 0.5), np.ceil(t_ref.astype(np.float64) - 0.5))
+        G = F32.astype(np.float64)[src]
+        PS = np.concatenate([np.zeros((1, 13)), np.cumsum(G, axis=0)])
+        PQ = np.concatenate([np.zeros((1, 13)), np.cumsum(G * G, axis=0)])
+        S, Q = PS[101:150] - PS[0:49], PQ[101:150] - PQ[0:49]
+        ok, k, tc, B = certify(S, Q, Q, F32, inv_scale)
+        assert not np.any(ok & (k_ref != k)), f"matrix {mi}: level 1 certified a wrong rounding"
+        with np.errstate(all="ignore"):
+            r = (np.abs(t_ref.astype(np.float64) - tc.astype(np.float64)) / B.astype(np.float64))[ok]
+        if r.size:
+            worst = max(worst, float(r.max()))
+        certified += int(ok.sum())
+        total += ok.size
+        # level 2 with the reference's own float mean
+        acc = np.zeros((49, 13), np.float32)
+        for w in range(101):
+            acc = (acc + G[np.arange(49) + w].astype(np.float32)).astype(np.float32)
+        mean = (acc / np.float32(101.0)).astype(np.float32)
+        M = S / 101.0
+        dm = mean.astype(np.float64) - M
+        V2 = (Q - S * M) + 101.0 * dm * dm
+        S2 = mean.astype(np.float64) * 101.0
+        ok2, k2, tc2, B2 = certify(S2, V2 + S2 * (S2 / 101.0), Q, F32, inv_scale, em_term=False)
+        assert not np.any(ok2 & (k_ref != k2)), f"matrix {mi}: level 2 certified a wrong rounding"
+        with np.errstate(all="ignore"):
+            r2 = (np.abs(t_ref.astype(np.float64) - tc2.astype(np.float64)) / B2.astype(np.float64))[ok2]
+        if r2.size:
+            worst = max(worst, float(r2.max()))
+    assert worst < 0.6, f"reference within {worst:.2f} B of the bound"
+    assert certified > 0.3 * total  # the guard conditions must not simply refuse everything
