@@ -354,6 +354,18 @@ def test_certified_cmvn_shortcut_is_bit_identical(name, impulses, synth):
         x = (d[:8192].to(torch.float32) / 32768.0).contiguous()
         assert torch.equal(imp.run_classifier_device(x), p0[:8192])
         assert np.array_equal(imp.run_classifier(clips.astype(np.float32) / np.float32(32768)), g["probs"])
+        # float samples no int16 source produces (inf, NaN, huge, denormal-small): the bound must refuse, never mis-certify
+        bad = x[:64].clone()
+        for i, v in enumerate([float("inf"), float("-inf"), float("nan"), 1e30, -3e38, 1e-30, 1e-42, 65504.0]):
+            bad[i, 100 + 37 * i] = v
+            bad[8 + i, 320 * (3 + 5 * i):320 * (4 + 5 * i)] = v
+            bad[16 + i] *= v if np.isfinite(v) else 1.0
+        with_shortcut = imp.run_classifier_device(bad).clone()
+        imp.set_cmvn_shortcut(False)
+        without = imp.run_classifier_device(bad).clone()
+        imp.set_cmvn_shortcut(True)
+        torch.cuda.synchronize()
+        assert torch.equal(with_shortcut, without)
     finally:
         imp.set_cmvn_shortcut(True)
         imp.set_tensor_core(True)
