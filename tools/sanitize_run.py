@@ -30,7 +30,7 @@ for knobs in ({"work_claiming": False}, {"cmvn_shortcut": False}, {"tensor_core"
     torch.cuda.synchronize()
     assert torch.equal(got, want), knobs
 imp.close()
-for name in (("l476",) if quick else ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32")):
+for name in (("l476", "zip6") if quick else ("l476", "l432", "gsc12", "dw3", "zip6", "l476f32")):
     imp = m.Impulse(name)
     p16 = imp.run_classifier_device(d16)
     p32 = imp.run_classifier_device(d32)
