@@ -126,3 +126,17 @@ def test_cmvn_rounding_trick_equals_the_float_cast(tmp_path):
     out = subprocess.run([exe, "30000000"], check=True, capture_output=True, text=True).stdout
     m = re.search(r"checked=(\d+) mismatches=(\d+) exact_ties=(\d+) float_denormal_sums=(\d+)", out)
     assert m and int(m.group(2)) == 0 and int(m.group(1)) > 10_000_000 and int(m.group(3)) > 100_000 and int(m.group(4)) > 10_000, out
+
+
+def test_tuning_knobs_are_exported_and_validate_their_arguments(eikws):
+    """the schedule / lowering knobs tools/ab.py and the parity tests flip (not part of the public header): present, and a null
+    handle or an out-of-range value is refused instead of being stored"""
+    lib = eikws.load_library()
+    for name in ("eikws_set_cmvn_shortcut", "eikws_set_work_claiming", "eikws_set_tensor_core", "eikws_set_clips_per_cta",
+                 "eikws_set_ctas_per_sm", "eikws_set_skew_ns", "eikws_classify_taps_i16_device"):
+        assert hasattr(lib, name), name
+    for name in ("eikws_set_cmvn_shortcut", "eikws_set_work_claiming", "eikws_set_tensor_core", "eikws_set_clips_per_cta"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+        assert fn(None, 1) != 0
