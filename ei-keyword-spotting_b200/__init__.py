@@ -82,6 +82,18 @@ def load_library() -> C.CDLL:
     L.eikws_streams_push_i16_host.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32)]
     L.eikws_streams_push_i16_device.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32), vp]
     L.eikws_debug_host_plan.argtypes = [C.c_char_p, sz, vp, vp, vp, i32, C.POINTER(i32)]
+    L.eikws_debug_cmvn_quantise_host.argtypes = [vp, vp, sz, i32, vp]
+    L.eikws_multi_create.argtypes = [C.c_char_p, sz, C.POINTER(i32), i32, C.POINTER(vp)]
+    L.eikws_multi_destroy.argtypes = [vp]
+    L.eikws_multi_device_count.argtypes = [vp]
+    L.eikws_multi_handle.restype = vp
+    L.eikws_multi_handle.argtypes = [vp, i32]
+    L.eikws_multi_shard.argtypes = [vp, sz, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.eikws_multi_classify_i16_host.argtypes = [vp, vp, sz, vp]
+    L.eikws_multi_classify_f32_host.argtypes = [vp, vp, sz, vp]
+    L.eikws_host_alloc.restype = vp
+    L.eikws_host_alloc.argtypes = [sz]
+    L.eikws_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -203,6 +215,14 @@ class Impulse:
         _check(self._lib.eikws_infer_host(self._h, _np_ptr(features), features.shape[0], _np_ptr(out)))
         return out
 
+    def debug_cmvn_quantise(self, cepstra: np.ndarray, shortcut: bool) -> np.ndarray:
+        """tests only: CMVN + int8 input quantisation of pre-CMVN cepstra [n,49,13] on the device -> int8 [n,637];
+        shortcut=True runs the certified path of the default classify kernel, False every chain with the reference's sequence"""
+        cep = np.ascontiguousarray(cepstra, dtype=np.float32).reshape(-1, self.feature_count)
+        q = np.empty(cep.shape, np.int8)
+        _check(self._lib.eikws_debug_cmvn_quantise_host(self._h, _np_ptr(cep), cep.shape[0], 1 if shortcut else 0, _np_ptr(q)))
+        return q
+
     # ---- device (torch) batch API: tensors already resident in HBM, asynchronous on the current stream -----
     def run_classifier_device(self, clips, out=None):
         import torch
@@ -280,6 +300,51 @@ class Impulse:
         out = torch.empty((n_clips, self.raw_sample_count), dtype=torch.int16, device=f"cuda:{self.device}")
         stream = C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)
         _check(self._lib.eikws_synth_i16_device(self._h, C.c_void_p(out.data_ptr()), n_clips, first_clip, seed, stream))
+        return out
+
+
+class MultiImpulse:
+    """One impulse replicated on several GPUs of the box (eikws_multi_*): host batches are sharded contiguously, one host
+    thread and stream pair per device, no exchange between devices."""
+
+    def __init__(self, model="l476", devices=None, n_devices=0):
+        self._lib = load_library()
+        self._blob = model_blob(model) if isinstance(model, str) else bytes(model)
+        h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self._lib.eikws_multi_create(self._blob, len(self._blob), arr, len(devices), C.byref(h)))
+        else:
+            _check(self._lib.eikws_multi_create(self._blob, len(self._blob), None, int(n_devices), C.byref(h)))
+        self._m = h
+        self.device_count = self._lib.eikws_multi_device_count(h)
+        self.label_count = self._lib.eikws_label_count(self._lib.eikws_multi_handle(h, 0))
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.eikws_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, n_clips: int, i: int):
+        first, count = C.c_size_t(0), C.c_size_t(0)
+        self._lib.eikws_multi_shard(self._m, n_clips, i, C.byref(first), C.byref(count))
+        return first.value, count.value
+
+    def run_classifier(self, clips: np.ndarray) -> np.ndarray:
+        clips = np.ascontiguousarray(clips).reshape(-1, N_SAMPLES)
+        out = np.empty((clips.shape[0], self.label_count), np.float32)
+        if clips.dtype == np.int16:
+            _check(self._lib.eikws_multi_classify_i16_host(self._m, _np_ptr(clips), clips.shape[0], _np_ptr(out)))
+        elif clips.dtype == np.float32:
+            _check(self._lib.eikws_multi_classify_f32_host(self._m, _np_ptr(clips), clips.shape[0], _np_ptr(out)))
+        else:
+            raise TypeError("clips must be int16 or float32")
         return out
 
 

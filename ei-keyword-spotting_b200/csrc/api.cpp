@@ -2,12 +2,14 @@
 // No CPU compute path exists here; every classify/features call launches the CUDA kernel or fails.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "eikws_b200.h"
@@ -33,9 +35,10 @@ struct eikws_handle {
     int work_claiming = 1;  // work-claiming schedule of the shortcut kernel (kDyn in kernels.cu)
     int cmvn_shortcut = 1;  // certified CMVN shortcut of the tensor-core variant (kernels.cu cmvn_certified; exact fallback inside the kernel)
     int tensor_core = 1;  // block 1 of the fused classifier as a tcgen05 UMMA (when the plan allows it; +2.4 %, profiles/r1_ab_tensor_core_block1.txt)
-    uint64_t launches = 0;
-    std::mutex mu;  // serialises the host-buffer and single-clip paths (they share staging buffers)
-    // staging for the host-buffer entry points
+    std::atomic<uint64_t> launches{0};
+    std::mutex mu;  // serialises the host-buffer and single-clip paths (they share staging buffers) from the first byte staged to the last result copied
+    // staging for the host-buffer entry points: a ring of kHostRing chunk slots per buffer (chunk i uses slot i % kHostRing on stream
+    // i % 2, so a slot is only ever reused by a later chunk of the SAME stream: stream order is the only synchronisation needed)
     void *d_in = nullptr;
     size_t d_in_bytes = 0;
     float *d_probs = nullptr;
@@ -47,6 +50,7 @@ struct eikws_handle {
     float *h_pinned = nullptr;  // one clip of floats for eikws_run_classifier_signal
     cudaStream_t stream = nullptr, stream2 = nullptr;
     size_t host_chunk_clips = 8192;  // host-buffer path: clips per pipelined chunk (262 MB of int16 PCM)
+    static constexpr size_t kHostRing = 4;  // chunk slots in flight (even: see above)
 };
 
 namespace {
@@ -226,7 +230,7 @@ const char *eikws_label(const eikws_handle *h, int i) {
     if (!h || i < 0 || i >= static_cast<int>(h->graph.labels.size())) return nullptr;
     return h->graph.labels[i].c_str();
 }
-uint64_t eikws_launch_count(const eikws_handle *h) { return h ? h->launches : 0; }
+uint64_t eikws_launch_count(const eikws_handle *h) { return h ? h->launches.load() : 0; }
 
 int eikws_set_ctas_per_sm(eikws_handle *h, int n) {  // tuning knob (not in the public header)
     if (!h || n < 1 || n > 8) return EIKWS_ERR_BAD_ARG;
@@ -314,55 +318,90 @@ int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n, uint64_t f
 
 // ---- host-buffer entry points (synchronous) ---------------------------------------------------------------
 // Host-buffer path: the batch is cut into chunks that alternate between two streams, so the H2D copy of chunk i+1
-// (PCIe) overlaps the kernel and the D2H of chunk i.  The staging buffers hold the whole batch; results land in place.
+// (PCIe) overlaps the kernel and the D2H of chunk i.  Device staging is a ring of kHostRing chunk slots (not the whole
+// batch): memory stays bounded for any n, results land in the caller's buffers in place.
+// The caller holds h->mu and has selected the device.
+static int host_run_locked(eikws_handle *h, const void *in, size_t in_bytes_per_clip, bool f32, const float *features_in, size_t n, bool run_nn,
+                           float *probs, float *features, int8_t *qfeatures) {
+    if (n == 0) return EIKWS_OK;
+    const size_t L = h->graph.labels.size(), F = h->graph.nn_input_frame_size;
+    int rc;
+    cudaError_t e;
+    if (!h->stream2 && (e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    const size_t chunk = h->host_chunk_clips;
+    const size_t slots = (n + chunk - 1) / chunk < eikws_handle::kHostRing ? (n + chunk - 1) / chunk : eikws_handle::kHostRing;
+    const size_t cap = (n < chunk ? n : chunk) * slots;  // clips the ring holds
+    if (features_in) {
+        if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, cap * F * 4))) return rc;
+    } else {
+        if ((rc = ensure(&h->d_in, &h->d_in_bytes, cap * in_bytes_per_clip))) return rc;
+        if (features && (rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, cap * F * 4))) return rc;
+    }
+    if (probs && (rc = ensure(reinterpret_cast<void **>(&h->d_probs), &h->d_probs_bytes, cap * L * 4))) return rc;
+    if (qfeatures && (rc = ensure(reinterpret_cast<void **>(&h->d_qfeat), &h->d_qfeat_bytes, cap * F))) return rc;
+    rc = EIKWS_OK;
+    size_t ci = 0;
+    for (size_t off = 0; off < n && rc == EIKWS_OK; off += chunk, ci++) {
+        const size_t m = n - off < chunk ? n - off : chunk;
+        const size_t so = (ci % slots) * chunk;  // first clip of this chunk's ring slot
+        cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
+        const void *d_src = nullptr;
+        if (features_in) {
+            if ((e = cudaMemcpyAsync(h->d_feat + so * F, features_in + off * F, m * F * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+                rc = cuda_fail(e, "H2D features");
+                break;
+            }
+        } else {
+            uint8_t *dst = static_cast<uint8_t *>(h->d_in) + so * in_bytes_per_clip;
+            if ((e = cudaMemcpyAsync(dst, static_cast<const uint8_t *>(in) + off * in_bytes_per_clip, m * in_bytes_per_clip, cudaMemcpyHostToDevice,
+                                     st)) != cudaSuccess) {
+                rc = cuda_fail(e, "H2D clips");
+                break;
+            }
+            d_src = dst;
+        }
+        rc = launch(h, d_src, f32, features_in ? h->d_feat + so * F : nullptr, m, run_nn, probs ? h->d_probs + so * L : nullptr,
+                    (features && !features_in) ? h->d_feat + so * F : nullptr, qfeatures ? h->d_qfeat + so * F : nullptr, st);
+        if (rc) break;
+        if (probs && (e = cudaMemcpyAsync(probs + off * L, h->d_probs + so * L, m * L * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H probs");
+        else if (features && !features_in &&
+                 (e = cudaMemcpyAsync(features + off * F, h->d_feat + so * F, m * F * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H features");
+        else if (qfeatures && (e = cudaMemcpyAsync(qfeatures + off * F, h->d_qfeat + so * F, m * F, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+            rc = cuda_fail(e, "D2H qfeatures");
+    }
+    // always drain both streams, also on an error path: queued D2H copies must not write into the caller's buffers after the return
+    const cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->stream2);
+    if (rc != EIKWS_OK) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "kernel execution");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "kernel execution");
+    return EIKWS_OK;
+}
 static int host_run(eikws_handle *h, const void *in, size_t in_bytes_per_clip, bool f32, const float *features_in, size_t n, bool run_nn,
                     float *probs, float *features, int8_t *qfeatures) {
     if (n == 0) return EIKWS_OK;
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
-    const size_t L = h->graph.labels.size(), F = h->graph.nn_input_frame_size;
-    int rc;
-    cudaError_t e;
-    if (!h->stream2 && (e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
-    if (features_in) {
-        if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
-    } else {
-        if ((rc = ensure(&h->d_in, &h->d_in_bytes, n * in_bytes_per_clip))) return rc;
-        if (features && (rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * F * 4))) return rc;
-    }
-    if (probs && (rc = ensure(reinterpret_cast<void **>(&h->d_probs), &h->d_probs_bytes, n * L * 4))) return rc;
-    if (qfeatures && (rc = ensure(reinterpret_cast<void **>(&h->d_qfeat), &h->d_qfeat_bytes, n * F))) return rc;
-    const size_t chunk = h->host_chunk_clips;
-    int ci = 0;
-    for (size_t off = 0; off < n; off += chunk, ci++) {
-        const size_t m = n - off < chunk ? n - off : chunk;
-        cudaStream_t st = (ci & 1) ? h->stream2 : h->stream;
-        const void *d_src = nullptr;
-        if (features_in) {
-            if ((e = cudaMemcpyAsync(h->d_feat + off * F, features_in + off * F, m * F * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-                return cuda_fail(e, "H2D features");
-        } else {
-            uint8_t *dst = static_cast<uint8_t *>(h->d_in) + off * in_bytes_per_clip;
-            if ((e = cudaMemcpyAsync(dst, static_cast<const uint8_t *>(in) + off * in_bytes_per_clip, m * in_bytes_per_clip, cudaMemcpyHostToDevice,
-                                     st)) != cudaSuccess)
-                return cuda_fail(e, "H2D clips");
-            d_src = dst;
-        }
-        rc = launch(h, d_src, f32, features_in ? h->d_feat + off * F : nullptr, m, run_nn, probs ? h->d_probs + off * L : nullptr,
-                    (features && !features_in) ? h->d_feat + off * F : nullptr, qfeatures ? h->d_qfeat + off * F : nullptr, st);
-        if (rc) return rc;
-        if (probs && (e = cudaMemcpyAsync(probs + off * L, h->d_probs + off * L, m * L * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-            return cuda_fail(e, "D2H probs");
-        if (features && !features_in &&
-            (e = cudaMemcpyAsync(features + off * F, h->d_feat + off * F, m * F * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-            return cuda_fail(e, "D2H features");
-        if (qfeatures && (e = cudaMemcpyAsync(qfeatures + off * F, h->d_qfeat + off * F, m * F, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
-            return cuda_fail(e, "D2H qfeatures");
-    }
-    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
-    if ((e = cudaStreamSynchronize(h->stream2)) != cudaSuccess) return cuda_fail(e, "kernel execution");
-    return EIKWS_OK;
+    if (!guard.ok) return fail(EIKWS_ERR_CUDA, "cudaSetDevice failed");
+    return host_run_locked(h, in, in_bytes_per_clip, f32, features_in, n, run_nn, probs, features, qfeatures);
 }
+// one clip pulled through the signal callback into the handle's pinned buffer, then classified / transformed -- the lock is held from
+// the first byte the callback writes to the last result byte copied back, so concurrent callers cannot see each other's clip
+}  // extern "C"
+template <class Run>
+static int signal_run(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, Run run) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(EIKWS_ERR_CUDA, "cudaSetDevice failed");
+    if (!h->h_pinned) {
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+    }
+    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
+    return run(h->h_pinned);
+}
+extern "C" {
 
 int eikws_classify_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *probs) {
     if (!h || !pcm || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
@@ -419,10 +458,8 @@ int eikws_mfe_f32_device(eikws_handle *h, const float *d_samples, size_t n, floa
     DeviceGuard guard(h->device);
     return launch_mfe_on(h, d_samples, true, n, d_features, static_cast<cudaStream_t>(stream));
 }
-static int mfe_host(eikws_handle *h, const void *in, size_t bytes_per_clip, bool f32, size_t n, float *features) {
+static int mfe_host_locked(eikws_handle *h, const void *in, size_t bytes_per_clip, bool f32, size_t n, float *features) {
     if (n == 0) return EIKWS_OK;
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->device);
     const size_t F = static_cast<size_t>(kFrames) * kFilters;
     int rc;
     cudaError_t e;
@@ -433,6 +470,13 @@ static int mfe_host(eikws_handle *h, const void *in, size_t bytes_per_clip, bool
     if ((e = cudaMemcpyAsync(features, h->d_feat, n * F * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return cuda_fail(e, "D2H features");
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
     return EIKWS_OK;
+}
+static int mfe_host(eikws_handle *h, const void *in, size_t bytes_per_clip, bool f32, size_t n, float *features) {
+    if (n == 0) return EIKWS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(EIKWS_ERR_CUDA, "cudaSetDevice failed");
+    return mfe_host_locked(h, in, bytes_per_clip, f32, n, features);
 }
 int eikws_mfe_i16_host(eikws_handle *h, const int16_t *pcm, size_t n, float *features) {
     if (!h || !pcm || !features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
@@ -455,16 +499,8 @@ int eikws_extract_mfe_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t
         return fail(EIKWS_ERR_UNSUPPORTED, "MFE block: only the geometry of the impulse's MFCC block is implemented");
     if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
     if (capacity < static_cast<size_t>(kFrames) * kFilters) return fail(EIKWS_ERR_DSP, "MFE block: output matrix too small (ei_run_dsp.h:384-388)");
-    {
-        std::lock_guard<std::mutex> lk(h->mu);
-        DeviceGuard guard(h->device);
-        if (!h->h_pinned) {
-            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-        }
-    }
-    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
-    return eikws_mfe_f32_host(h, h->h_pinned, 1, features);
+    return signal_run(h, get_data, total_length,
+                      [&](const float *clip) { return mfe_host_locked(h, clip, static_cast<size_t>(kSamples) * 4, true, 1, features); });
 }
 
 // ---- single clip through the reference's pull callback -----------------------------------------------------
@@ -478,16 +514,9 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
     // EI_CLASSIFIER_RAW_SAMPLE_COUNT samples.
     if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
     auto t0 = std::chrono::steady_clock::now();
-    {
-        std::lock_guard<std::mutex> lk(h->mu);
-        DeviceGuard guard(h->device);
-        if (!h->h_pinned) {
-            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-        }
-    }
-    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
-    int rc = eikws_classify_f32_host(h, h->h_pinned, 1, values);
+    int rc = signal_run(h, get_data, total_length, [&](const float *clip) {
+        return host_run_locked(h, clip, static_cast<size_t>(kSamples) * 4, true, nullptr, 1, true, values, nullptr, nullptr);
+    });
     auto t1 = std::chrono::steady_clock::now();
     // the fused kernel does DSP and classification in one launch; the whole latency is reported as dsp
     if (t_dsp_ms) *t_dsp_ms = static_cast<int>(std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
@@ -498,16 +527,9 @@ int eikws_run_classifier_signal(eikws_handle *h, eikws_get_data_fn get_data, siz
 int eikws_extract_mfcc_signal(eikws_handle *h, eikws_get_data_fn get_data, size_t total_length, float *features) {
     if (!h || !get_data || !features) return fail(EIKWS_ERR_BAD_ARG, "null argument");
     if (total_length != h->graph.raw_sample_count) return fail(EIKWS_ERR_DSP, "signal length does not match EI_CLASSIFIER_RAW_SAMPLE_COUNT");
-    {
-        std::lock_guard<std::mutex> lk(h->mu);
-        DeviceGuard guard(h->device);
-        if (!h->h_pinned) {
-            cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&h->h_pinned), sizeof(float) * kSamples);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-        }
-    }
-    if (get_data(0, total_length, h->h_pinned) != 0) return fail(EIKWS_ERR_DSP, "signal get_data callback failed");
-    return eikws_features_f32_host(h, h->h_pinned, 1, features, nullptr);
+    return signal_run(h, get_data, total_length, [&](const float *clip) {
+        return host_run_locked(h, clip, static_cast<size_t>(kSamples) * 4, true, nullptr, 1, false, nullptr, features, nullptr);
+    });
 }
 
 // ---- continuous mode: many audio streams advancing one slice per call ---------------------------------------------
@@ -543,9 +565,14 @@ int eikws_streams_reset(eikws_streams *s) {
     DeviceGuard guard(s->h->device);
     const size_t L = s->h->graph.labels.size();
     cudaError_t e;
-    if ((e = cudaMemset(s->d_features, 0, s->n * kFeatures * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
-    if ((e = cudaMemset(s->d_maf_buf, 0, s->n * L * s->maf_len * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
-    if ((e = cudaMemset(s->d_maf_sum, 0, s->n * L * 4)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    // Stream-ordering contract: the state is cleared on the handle's own stream and the call returns only after the clears have
+    // completed, so a following eikws_streams_push_*_device on ANY stream sees the power-up state.  (A plain cudaMemset runs on
+    // the legacy default stream, which the non-blocking compute streams do not synchronise with.)
+    cudaStream_t st = s->h->stream;
+    if ((e = cudaMemsetAsync(s->d_features, 0, s->n * kFeatures * 4, st)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    if ((e = cudaMemsetAsync(s->d_maf_buf, 0, s->n * L * s->maf_len * 4, st)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    if ((e = cudaMemsetAsync(s->d_maf_sum, 0, s->n * L * 4, st)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail(e, "cudaMemset");
     s->first_run = false;
     s->window_full = false;
     s->slice_offset = 0;
@@ -596,18 +623,21 @@ static int streams_push_device(eikws_streams *s, const void *d_slices, bool f32,
     eikws_handle *h = s->h;
     DeviceGuard guard(h->device);
     const MfccConfig &c = h->graph.mfcc;
+    // the stream's new bookkeeping is computed into locals and committed only after the launch has succeeded, so a refused or
+    // failed call leaves host state and device window in step
     int total_length = s->slice_size;
     if (s->first_run) total_length += static_cast<int>(c.frame_length * static_cast<float>(c.sample_rate));  // ei_run_dsp.h:322-324
-    s->first_run = true;
     const int n_frames = (total_length - kFrameLen) / kFrameStride;  // calculate_no_of_stack_frames (processing.hpp:260-284)
     const size_t feature_size = static_cast<size_t>(n_frames) * kCepstra;
     if (s->slice_offset + feature_size > kFeatures) return fail(EIKWS_ERR_DSP, "Would write outside feature buffer");
     const size_t offset_now = s->slice_offset;
-    if (!s->window_full) {  // ei_run_classifier.h:230-238
-        s->slice_offset += feature_size;
-        if (s->slice_offset > kFeatures - feature_size) {
-            s->window_full = true;
-            s->slice_offset -= feature_size;
+    size_t new_offset = s->slice_offset;
+    bool new_full = s->window_full;
+    if (!new_full) {  // ei_run_classifier.h:230-238
+        new_offset += feature_size;
+        if (new_offset > kFeatures - feature_size) {
+            new_full = true;
+            new_offset -= feature_size;
         }
     }
     ContinuousArgs a;
@@ -623,7 +653,7 @@ static int streams_push_device(eikws_streams *s, const void *d_slices, bool f32,
     a.maf_buf = s->d_maf_buf;
     a.maf_sum = s->d_maf_sum;
     a.slice_offset = static_cast<int>(offset_now);
-    a.window_full = s->window_full ? 1 : 0;
+    a.window_full = new_full ? 1 : 0;
     a.maf_idx = s->maf_idx;
     a.maf_len = s->maf_len;
     a.cmvn_certified = h->cmvn_shortcut != 0;
@@ -635,8 +665,11 @@ static int streams_push_device(eikws_streams *s, const void *d_slices, bool f32,
     cudaError_t e = launch_continuous(a);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     h->launches++;
-    *has_result = s->window_full ? 1 : 0;
-    if (s->window_full && ++s->maf_idx >= s->maf_len) s->maf_idx = 0;
+    s->first_run = true;
+    s->slice_offset = new_offset;
+    s->window_full = new_full;
+    *has_result = new_full ? 1 : 0;
+    if (new_full && ++s->maf_idx >= s->maf_len) s->maf_idx = 0;
     return EIKWS_OK;
 }
 
@@ -694,6 +727,153 @@ int eikws_debug_stage_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t 
     if (!rc && (e = cudaStreamSynchronize(h->stream)) != cudaSuccess) rc = cuda_fail(e, "kernel execution");
     cudaFree(d_taps);
     return rc;
+}
+
+// tests only: CMVN + input quantisation of caller-supplied pre-CMVN cepstra [n][49][13] (host) -> int8 features [n][637] (host);
+// shortcut != 0 runs the certified path of the default classify kernel (cmvn_certified / cmvn_resolve), 0 every chain exactly
+int eikws_debug_cmvn_quantise_host(eikws_handle *h, const float *cepstra, size_t n, int shortcut, int8_t *q) {
+    if (!h || !cepstra || !q) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    if (!h->host.dev.mfcc.input_is_int8) return fail(EIKWS_ERR_UNSUPPORTED, "the model has no quantised input tensor");
+    if (n == 0) return EIKWS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    int rc;
+    cudaError_t e;
+    if ((rc = ensure(reinterpret_cast<void **>(&h->d_feat), &h->d_feat_bytes, n * kFeatures * 4))) return rc;
+    if ((rc = ensure(reinterpret_cast<void **>(&h->d_qfeat), &h->d_qfeat_bytes, n * kFeatures))) return rc;
+    if ((e = cudaMemcpyAsync(h->d_feat, cepstra, n * kFeatures * 4, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return cuda_fail(e, "H2D");
+    if ((e = launch_debug_cmvn_quantise(h->dev.d_plan, h->d_feat, n, shortcut, h->d_qfeat, h->stream)) != cudaSuccess) return cuda_fail(e, "kernel launch");
+    h->launches++;
+    if ((e = cudaMemcpyAsync(q, h->d_qfeat, n * kFeatures, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) return cuda_fail(e, "D2H");
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return cuda_fail(e, "kernel execution");
+    return EIKWS_OK;
+}
+
+// ---- several GPUs of one box behind one call ----------------------------------------------------------------------------
+// The application's loop (nucleo-l476-keyword-spotting/Core/Src/main.cpp:190-194) classifies one window after the other on one
+// core; a batch host shards its clips over the box instead.  Clips are independent, so device d of D gets the contiguous range
+// [d*n/D, (d+1)*n/D) (sizes differ by at most one clip), one host thread and one pair of streams per device, no exchange
+// between devices; results land in place.
+struct eikws_multi {
+    std::vector<eikws_handle *> hs;
+};
+
+static void shard_range(size_t n, size_t parts, size_t i, size_t *lo, size_t *hi) {
+    const size_t base = n / parts, rem = n % parts;
+    *lo = i * base + (i < rem ? i : rem);
+    *hi = *lo + base + (i < rem ? 1 : 0);
+}
+
+void eikws_multi_destroy(eikws_multi *m) {
+    if (!m) return;
+    for (eikws_handle *h : m->hs) eikws_destroy(h);
+    delete m;
+}
+
+int eikws_multi_create(const void *model_blob, size_t bytes, const int *devices, int n_devices, eikws_multi **out) {
+    if (!out) return fail(EIKWS_ERR_BAD_ARG, "null output argument");
+    *out = nullptr;
+    std::vector<int> devs;
+    if (devices) {
+        if (n_devices < 1) return fail(EIKWS_ERR_BAD_ARG, "empty device list");
+        devs.assign(devices, devices + n_devices);
+    } else {  // every visible device (n_devices > 0 caps the count)
+        int nd = 0;
+        cudaError_t e = cudaGetDeviceCount(&nd);
+        if (e != cudaSuccess || nd <= 0) return fail(EIKWS_ERR_CUDA, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+        if (n_devices > 0 && n_devices < nd) nd = n_devices;
+        for (int d = 0; d < nd; d++) devs.push_back(d);
+    }
+    for (size_t i = 0; i < devs.size(); i++)
+        for (size_t j = 0; j < i; j++)
+            if (devs[i] == devs[j]) return fail(EIKWS_ERR_BAD_ARG, "device listed twice");
+    eikws_multi *m = new (std::nothrow) eikws_multi();
+    if (!m) return fail(EIKWS_ERR_ALLOC_FAILED, "out of memory");
+    for (int d : devs) {
+        eikws_handle *h = nullptr;
+        int rc = eikws_create(model_blob, bytes, d, &h);
+        if (rc != EIKWS_OK) {
+            eikws_multi_destroy(m);
+            return rc;  // eikws_create has set the message
+        }
+        m->hs.push_back(h);
+    }
+    *out = m;
+    return EIKWS_OK;
+}
+
+int eikws_multi_device_count(const eikws_multi *m) { return m ? static_cast<int>(m->hs.size()) : 0; }
+eikws_handle *eikws_multi_handle(eikws_multi *m, int i) { return (m && i >= 0 && i < static_cast<int>(m->hs.size())) ? m->hs[i] : nullptr; }
+void eikws_multi_shard(const eikws_multi *m, size_t n_clips, int i, size_t *first, size_t *count) {
+    size_t lo = 0, hi = 0;
+    if (m && i >= 0 && i < static_cast<int>(m->hs.size())) shard_range(n_clips, m->hs.size(), static_cast<size_t>(i), &lo, &hi);
+    if (first) *first = lo;
+    if (count) *count = hi - lo;
+}
+
+}  // extern "C"
+template <class Fn>
+static int multi_run(eikws_multi *m, size_t n, Fn per_device) {
+    const size_t D = m->hs.size();
+    std::vector<int> rcs(D, EIKWS_OK);
+    std::vector<std::string> errs(D);
+    std::vector<std::thread> th;
+    th.reserve(D);
+    for (size_t d = 0; d < D; d++) {
+        th.emplace_back([&, d]() {
+            size_t lo, hi;
+            shard_range(n, D, d, &lo, &hi);
+            if (hi == lo) return;
+            rcs[d] = per_device(m->hs[d], lo, hi - lo);
+            if (rcs[d] != EIKWS_OK) errs[d] = t_err;  // the message lives in the worker's thread-local slot
+        });
+    }
+    for (std::thread &t : th) t.join();
+    for (size_t d = 0; d < D; d++)
+        if (rcs[d] != EIKWS_OK) return fail(rcs[d], "device " + std::to_string(m->hs[d]->device) + ": " + errs[d]);
+    return EIKWS_OK;
+}
+extern "C" {
+
+int eikws_multi_classify_i16_host(eikws_multi *m, const int16_t *pcm, size_t n, float *probs) {
+    if (!m || m->hs.empty() || !pcm || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    const size_t L = m->hs[0]->graph.labels.size();
+    return multi_run(m, n, [&](eikws_handle *h, size_t first, size_t count) {
+        return eikws_classify_i16_host(h, pcm + first * kSamples, count, probs + first * L);
+    });
+}
+int eikws_multi_classify_f32_host(eikws_multi *m, const float *samples, size_t n, float *probs) {
+    if (!m || m->hs.empty() || !samples || !probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    const size_t L = m->hs[0]->graph.labels.size();
+    return multi_run(m, n, [&](eikws_handle *h, size_t first, size_t count) {
+        return eikws_classify_f32_host(h, samples + first * kSamples, count, probs + first * L);
+    });
+}
+// Device-resident shards: d_pcm[i] / d_probs[i] live on device i of the set and hold n_clips[i] clips; every launch is
+// asynchronous on streams[i] (NULL array or entry = that device's default stream).  One host thread issues all of them.
+int eikws_multi_classify_i16_device(eikws_multi *m, const int16_t *const *d_pcm, const size_t *n_clips, float *const *d_probs, void *const *streams) {
+    if (!m || m->hs.empty() || !d_pcm || !n_clips || !d_probs) return fail(EIKWS_ERR_BAD_ARG, "null argument");
+    for (size_t d = 0; d < m->hs.size(); d++) {
+        if (n_clips[d] == 0) continue;
+        int rc = eikws_classify_i16_device(m->hs[d], d_pcm[d], n_clips[d], d_probs[d], streams ? streams[d] : nullptr);
+        if (rc != EIKWS_OK) return rc;
+    }
+    return EIKWS_OK;
+}
+
+// Page-locked host memory for a pure-C host (no CUDA headers needed): buffers handed to the *_host entry points are copied at
+// PCIe speed and asynchronously only when they are pinned; cudaHostAllocPortable makes them so for every device of the box.
+void *eikws_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaHostAlloc");
+        return nullptr;
+    }
+    return p;
+}
+void eikws_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 // ---- parity taps of host-side derived data (tests only; no GPU needed) ------------------------------------------

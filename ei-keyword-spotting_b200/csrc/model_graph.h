@@ -82,5 +82,7 @@ struct ModelGraph {
 void serialize_model(const ModelGraph &g, std::vector<uint8_t> &out);
 // returns false and fills err on malformed input
 bool parse_model(const void *blob, size_t bytes, ModelGraph &g, std::string &err);
+// structural checks on an untrusted graph (run by parse_model): indices, shapes vs byte sizes, per-operator arity, divisors
+bool validate_model(const ModelGraph &g, std::string &err);
 
 }  // namespace eikws

@@ -96,13 +96,14 @@ void mel_filterbank(std::vector<float> &fb, int filters, int bins, uint32_t fs, 
     for (int i = 0; i < filters; i++) {
         const int left = bin[i], middle = bin[i + 1], right = bin[i + 2];
         const int zn = right - left + 1;
+        if (zn <= 0) continue;
         std::vector<float> z(zn);
         linspace(static_cast<float>(left), static_cast<float>(right), zn, z.data());
         for (int zx = 0; zx < zn; zx++) {
             float x = z[zx], o = 0.0f;  // functions::triangle (functions.hpp:90-104)
             if (x > left && x <= middle) o = (x - left) / (middle - left);
             if (x < right && middle <= x) o = (right - x) / (right - middle);
-            fb[static_cast<size_t>(left + zx) * filters + i] = o;
+            if (left + zx >= 0 && left + zx < bins) fb[static_cast<size_t>(left + zx) * filters + i] = o;  // (always true for a validated band)
         }
     }
 }
@@ -169,6 +170,12 @@ void activation_range_i8(int act, const TensorDesc &out, int32_t *lo, int32_t *h
         *lo = std::max(-128, quantize(-1.0f));
         *hi = std::min(127, quantize(1.0f));
     }
+}
+
+// acc = sum w*(x + in_offset) = sum w*x + in_offset*sum w with in_offset = -in_zp: the constant part is folded into the bias.
+// int32 accumulators wrap like the reference's on x86; done in 64 bits here so that a hostile bias cannot trigger signed overflow
+int32_t fold_bias(int32_t bias, int32_t in_zp, int32_t wsum) {
+    return static_cast<int32_t>(static_cast<uint32_t>(static_cast<int64_t>(bias) - static_cast<int64_t>(in_zp) * static_cast<int64_t>(wsum)));
 }
 
 int same_or_valid_pad(int padding, int stride, int dilation, int in, int filt) {  // padding.h:32-57
@@ -626,9 +633,13 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                     wsum += w[oc * K + k];
                 }
                 // acc = sum w*(x + in_offset) = sum w*x + in_offset*sum w, with in_offset = -in_zp
-                bias[oc] = (bsrc ? bsrc[oc] : 0) + (-op.in_zp) * wsum;
+                bias[oc] = fold_bias(bsrc ? bsrc[oc] : 0, op.in_zp, wsum);
                 int sh;
                 quantize_multiplier(eff[oc], &mult[oc], &sh);
+                if (!(eff[oc] >= 0.0) || sh < -31 || sh > 30) {  // also refuses NaN: the shifts below would be undefined
+                    err = "conv/fc: requantisation multiplier out of range";
+                    return EIKWS_ERR_UNSUPPORTED;
+                }
                 shift[oc] = sh;
             }
             {
@@ -680,6 +691,10 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             quantize_multiplier(static_cast<double>(in1.scale()) / twice_max, &m1, &s1);
             quantize_multiplier(static_cast<double>(in2.scale()) / twice_max, &m2, &s2);
             quantize_multiplier(twice_max / ((1 << left_shift) * static_cast<double>(out.scale())), &mo, &so);
+            if (s1 > 0 || s2 > 0 || so > 0 || s1 < -31 || s2 < -31 || so < -31) {  // MultiplyByQuantizedMultiplierSmallerThanOneExp needs exponents <= 0
+                err = "add: operand / output scales out of the range the fixed-point rescaling supports";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
             int32_t lo, hi;
             activation_range_i8(n.params[0], out, &lo, &hi);
             std::vector<uint8_t> lut(static_cast<size_t>(cst.bytes) * 256);
@@ -741,6 +756,10 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             int32_t mult;
             int left_shift;
             quantize_multiplier(rm, &mult, &left_shift);
+            if (!(rm > 0.0) || left_shift < 0 || left_shift > 30) {
+                err = "softmax: beta * input scale out of range";
+                return EIKWS_ERR_UNSUPPORTED;
+            }
             const double max_rescaled = 1.0 * ((1 << kBits) - 1) * static_cast<double>(1ll << (31 - kBits)) / static_cast<double>(1ll << left_shift);
             const int diff_min = -1 * static_cast<int>(std::floor(max_rescaled));
             std::vector<int32_t> elut(256);
@@ -851,7 +870,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                         reinterpret_cast<uint8_t *>(packed.data())[(static_cast<size_t>(oc) * cv.kw + kx) * cp + c2] = static_cast<uint8_t>(wv);
                         wsum += wv;
                     }
-                bias[oc] = cs->raw_bias[oc] + (-cv.in_zp) * wsum;
+                bias[oc] = fold_bias(cs->raw_bias[oc], cv.in_zp, wsum);
             }
             b.bind(st.weights, b.push(packed.data(), packed.size() * 4));
             b.bind(st.bias, b.push(bias.data(), bias.size() * 4));
@@ -894,7 +913,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 for (int oc = 0; oc < fc.out_c; oc++) {
                     int32_t wsum = 0;
                     for (int d = 0; d < fc.in_c; d++) wsum += cs->w[oc * fc.in_c + d];
-                    fbias[oc] = cs->raw_bias[oc] + (-fc.in_zp) * wsum;
+                    fbias[oc] = fold_bias(cs->raw_bias[oc], fc.in_zp, wsum);
                 }
                 b.bind(fu.fc_w, b.push(cs->w, static_cast<size_t>(fc.out_c) * fc.in_c));
                 b.bind(fu.fc_bias, b.push(fbias.data(), fbias.size() * 4));
@@ -942,7 +961,10 @@ cudaError_t upload_plan(const HostPlan &hp, DevicePlan &dp) {
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(dp.d_plan, &img, sizeof(DevPlan), cudaMemcpyHostToDevice);
     dp.nn_smem_bytes = hp.nn_smem_bytes;
-    return e;
+    if (e != cudaSuccess) return e;
+    // pageable cudaMemcpy may return before the DMA has landed, and the kernels run on non-blocking streams that do not
+    // synchronise with the default stream: make the plan globally visible before the handle exists
+    return cudaDeviceSynchronize();
 }
 
 void free_plan(DevicePlan &dp) {

@@ -18,6 +18,7 @@
 #ifndef _EDGE_IMPULSE_RUN_CLASSIFIER_H_
 #define _EDGE_IMPULSE_RUN_CLASSIFIER_H_
 
+#include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,17 +28,42 @@
 #include "../dsp/numpy_types.h"
 #include "../porting/ei_classifier_porting.h"
 #include "ei_classifier_types.h"
-#include "ei_model_types.h"
-#include "ei_run_dsp.h"
 #include "eikws_b200.h"
-#include "model-parameters/dsp_blocks.h"
-#include "tflite-model/trained_model_compiled.h"
 
 #if EI_CLASSIFIER_INFERENCING_ENGINE != EI_CLASSIFIER_TFLITE || EI_CLASSIFIER_COMPILED != 1
 #error "eikws-b200 accelerates EON-compiled TFLite impulses (EI_CLASSIFIER_INFERENCING_ENGINE == EI_CLASSIFIER_TFLITE, EI_CLASSIFIER_COMPILED == 1)"
 #endif
 
-#ifdef __cplusplus
+#ifndef __cplusplus
+/* ---- C translation units ---------------------------------------------------------------------------------------------
+ * The reference declares run_classifier `extern "C"` but defines it inside a C++ header (anonymous namespace, default
+ * argument: reference :106-108, :650-653), and its README has users delete the SDK's C wrapper ei_run_classifier_c.*
+ * (README.md:185), so a pure-C firmware-style host cannot call it as shipped.  Here a .c file includes this header (exactly
+ * ONE translation unit of the program may, like the reference: model_metadata.h defines globals), gets the declarations
+ * below, and the program links
+ *     edge-impulse-sdk/classifier/ei_run_classifier_c.cpp   (C++ shim, defines these symbols with C linkage)
+ *     tflite-model/trained_model_compiled.cpp               (the unmodified generated model)
+ *     -leikws_b200
+ * `debug` is explicit in C (no default arguments); signal_t::get_data is the plain function pointer flavour
+ * (EIDSP_SIGNAL_C_FN_POINTER == 1, reference numpy_types.h:242-249).  See examples/static_buffer.c. */
+EI_IMPULSE_ERROR run_classifier(signal_t *signal, ei_impulse_result_t *result, bool debug);
+EI_IMPULSE_ERROR run_classifier_continuous(signal_t *signal, ei_impulse_result_t *result, bool debug);
+void run_classifier_init(void);
+/* batch extension: n_clips contiguous clips of EI_CLASSIFIER_RAW_SAMPLE_COUNT samples in host memory (pin it with
+ * eikws_host_alloc for full PCIe speed); sharded over the devices given to ei_b200_init */
+EI_IMPULSE_ERROR run_classifier_batch_i16(const int16_t *pcm, size_t n_clips, ei_impulse_result_t *results);
+EI_IMPULSE_ERROR run_classifier_batch_f32(const float *samples, size_t n_clips, ei_impulse_result_t *results);
+/* optional: choose the GPUs (devices == NULL: the first n_devices visible ones, n_devices <= 0: all of them).  Without it the
+ * first call lowers the impulse on device $EIKWS_DEVICE (default 0).  ei_b200_shutdown releases every device resource. */
+EI_IMPULSE_ERROR ei_b200_init(const int *devices, int n_devices);
+void ei_b200_shutdown(void);
+#else /* __cplusplus */
+
+#include "ei_model_types.h"
+#include "ei_run_dsp.h"
+#include "model-parameters/dsp_blocks.h"
+#include "tflite-model/trained_model_compiled.h"
+
 using ei::matrix_t;
 using ei::signal_t;
 
@@ -48,15 +74,11 @@ static void *eikws_dropin_input_thunk(int i) { return trained_model_input(i); }
 static void *eikws_dropin_output_thunk(int i) { return trained_model_output(i); }
 static int eikws_dropin_reset_thunk(void (*f)(void *)) { return (int)trained_model_reset(f); }
 
-/* Lowers the impulse on first use; returns NULL (after printing the reason) when that fails. */
-static eikws_handle *eikws_dropin_handle() {
-    static eikws_handle *handle = NULL;
-    static bool tried = false;
-    if (tried) return handle;
-    tried = true;
+/* Runs the generated trained_model_init() against the library's recording operators and serialises the captured impulse. */
+static int eikws_dropin_capture(void **blob, size_t *bytes) {
     if (ei_dsp_blocks_size != 1) {
         ei_printf("ERR: eikws-b200 supports impulses with exactly one (MFCC) DSP block\n");
-        return NULL;
+        return EIKWS_ERR_UNSUPPORTED;
     }
     const ei_dsp_config_mfcc_t *c = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
     eikws_compiled_model_t cm;
@@ -79,20 +101,32 @@ static eikws_handle *eikws_dropin_handle() {
     cm.mfcc_high_frequency = c->high_frequency;
     cm.mfcc_pre_cof = c->pre_cof;
     cm.mfcc_pre_shift = c->pre_shift;
+    int rc = eikws_model_from_compiled(&cm, blob, bytes);
+    if (rc != EIKWS_OK) ei_printf("ERR: eikws-b200 could not capture the compiled model: %s\n", eikws_last_error());
+    return rc;
+}
+
+/* process-wide state, like the reference's statics: the device set of ei_b200_init (or the single lazily created handle) */
+static eikws_multi *eikws_dropin_devices = NULL;
+static eikws_handle *eikws_dropin_single = NULL;
+static bool eikws_dropin_tried = false;
+
+/* Lowers the impulse on first use; returns NULL (after printing the reason) when that fails. */
+static eikws_handle *eikws_dropin_handle() {
+    if (eikws_dropin_devices) return eikws_multi_handle(eikws_dropin_devices, 0);
+    if (eikws_dropin_tried) return eikws_dropin_single;
+    eikws_dropin_tried = true;
     void *blob = NULL;
     size_t bytes = 0;
-    if (eikws_model_from_compiled(&cm, &blob, &bytes) != EIKWS_OK) {
-        ei_printf("ERR: eikws-b200 could not capture the compiled model: %s\n", eikws_last_error());
-        return NULL;
-    }
+    if (eikws_dropin_capture(&blob, &bytes) != EIKWS_OK) return NULL;
     const char *dev = getenv("EIKWS_DEVICE");
-    int rc = eikws_create(blob, bytes, dev ? atoi(dev) : 0, &handle);
+    int rc = eikws_create(blob, bytes, dev ? atoi(dev) : 0, &eikws_dropin_single);
     eikws_free(blob);
     if (rc != EIKWS_OK) {
         ei_printf("ERR: eikws-b200 could not create the device plan (%d): %s\n", rc, eikws_last_error());
-        handle = NULL;
+        eikws_dropin_single = NULL;
     }
-    return handle;
+    return eikws_dropin_single;
 }
 
 /* signal_t::get_data may be a std::function (EIDSP_SIGNAL_C_FN_POINTER == 0, the SDK default); the C ABI takes a
@@ -240,13 +274,19 @@ extern "C" EI_IMPULSE_ERROR run_classifier(signal_t *signal, ei_impulse_result_t
     return EI_IMPULSE_OK;
 }
 
-/* ---- batch extension: n_clips contiguous clips of EI_CLASSIFIER_RAW_SAMPLE_COUNT samples (host memory) ---- */
-extern "C" EI_IMPULSE_ERROR run_classifier_batch_i16(const int16_t *pcm, size_t n_clips, ei_impulse_result_t *results) {
+/* ---- batch extension: n_clips contiguous clips of EI_CLASSIFIER_RAW_SAMPLE_COUNT samples (host memory), sharded over the
+ * devices of ei_b200_init when it was called ---- */
+static EI_IMPULSE_ERROR eikws_dropin_batch(const void *clips, bool f32, size_t n_clips, ei_impulse_result_t *results) {
     eikws_handle *h = eikws_dropin_handle();
     if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
     float *values = (float *)malloc(sizeof(float) * EI_CLASSIFIER_LABEL_COUNT * (n_clips ? n_clips : 1));
     if (!values) return EI_IMPULSE_ALLOC_FAILED;
-    int rc = eikws_classify_i16_host(h, pcm, n_clips, values);
+    int rc;
+    if (eikws_dropin_devices)
+        rc = f32 ? eikws_multi_classify_f32_host(eikws_dropin_devices, (const float *)clips, n_clips, values)
+                 : eikws_multi_classify_i16_host(eikws_dropin_devices, (const int16_t *)clips, n_clips, values);
+    else
+        rc = f32 ? eikws_classify_f32_host(h, (const float *)clips, n_clips, values) : eikws_classify_i16_host(h, (const int16_t *)clips, n_clips, values);
     for (size_t i = 0; rc == EIKWS_OK && i < n_clips; i++) {
         memset(&results[i].timing, 0, sizeof(results[i].timing));
         eikws_dropin_fill_result(&results[i], values + i * EI_CLASSIFIER_LABEL_COUNT, false);
@@ -254,18 +294,37 @@ extern "C" EI_IMPULSE_ERROR run_classifier_batch_i16(const int16_t *pcm, size_t 
     free(values);
     return eikws_dropin_error(rc);
 }
-
+extern "C" EI_IMPULSE_ERROR run_classifier_batch_i16(const int16_t *pcm, size_t n_clips, ei_impulse_result_t *results) {
+    return eikws_dropin_batch(pcm, false, n_clips, results);
+}
 extern "C" EI_IMPULSE_ERROR run_classifier_batch_f32(const float *samples, size_t n_clips, ei_impulse_result_t *results) {
-    eikws_handle *h = eikws_dropin_handle();
-    if (!h) return EI_IMPULSE_TFLITE_ARENA_ALLOC_FAILED;
-    float *values = (float *)malloc(sizeof(float) * EI_CLASSIFIER_LABEL_COUNT * (n_clips ? n_clips : 1));
-    if (!values) return EI_IMPULSE_ALLOC_FAILED;
-    int rc = eikws_classify_f32_host(h, samples, n_clips, values);
-    for (size_t i = 0; rc == EIKWS_OK && i < n_clips; i++) {
-        memset(&results[i].timing, 0, sizeof(results[i].timing));
-        eikws_dropin_fill_result(&results[i], values + i * EI_CLASSIFIER_LABEL_COUNT, false);
+    return eikws_dropin_batch(samples, true, n_clips, results);
+}
+
+/* ---- device set (the library owns its device buffers behind an init / teardown pair; the two-argument call
+ * sequence keeps working without it).  devices == NULL: the first n_devices visible GPUs (n_devices <= 0: all). ---- */
+extern "C" void ei_b200_shutdown(void) {
+    if (eikws_dropin_stream) eikws_streams_destroy(eikws_dropin_stream);
+    eikws_dropin_stream = NULL;
+    eikws_dropin_stream_started = false;
+    if (eikws_dropin_devices) eikws_multi_destroy(eikws_dropin_devices);
+    eikws_dropin_devices = NULL;
+    if (eikws_dropin_single) eikws_destroy(eikws_dropin_single);
+    eikws_dropin_single = NULL;
+    eikws_dropin_tried = false;
+}
+extern "C" EI_IMPULSE_ERROR ei_b200_init(const int *devices, int n_devices) {
+    ei_b200_shutdown();
+    void *blob = NULL;
+    size_t bytes = 0;
+    int rc = eikws_dropin_capture(&blob, &bytes);
+    if (rc != EIKWS_OK) return eikws_dropin_error(rc);
+    rc = eikws_multi_create(blob, bytes, devices, n_devices, &eikws_dropin_devices);
+    eikws_free(blob);
+    if (rc != EIKWS_OK) {
+        ei_printf("ERR: eikws-b200 could not create the device plans (%d): %s\n", rc, eikws_last_error());
+        eikws_dropin_devices = NULL;
     }
-    free(values);
     return eikws_dropin_error(rc);
 }
 

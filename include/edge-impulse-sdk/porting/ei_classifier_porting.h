@@ -33,17 +33,32 @@ void ei_printf_float(float f);
 
 #if !defined(EIKWS_NO_DEFAULT_PORTING)
 /* weak defaults: an application definition (as the firmware's main.cpp:536-554 provides) wins at link time */
+#if defined(__cplusplus) || defined(_POSIX_C_SOURCE) || defined(_GNU_SOURCE)
 __attribute__((weak)) EI_IMPULSE_ERROR ei_sleep(int32_t time_ms) {
     struct timespec ts = {time_ms / 1000, (long)(time_ms % 1000) * 1000000L};
     nanosleep(&ts, NULL);
     return EI_IMPULSE_OK;
 }
-__attribute__((weak)) EI_IMPULSE_ERROR ei_run_impulse_check_canceled() { return EI_IMPULSE_OK; }
 __attribute__((weak)) uint64_t ei_read_timer_us() {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (uint64_t)ts.tv_sec * 1000000ull + (uint64_t)ts.tv_nsec / 1000;
 }
+#else /* a strict ISO C11 translation unit (gcc -std=c11): the POSIX clock calls are hidden, C11's own are used */
+__attribute__((weak)) EI_IMPULSE_ERROR ei_sleep(int32_t time_ms) {
+    struct timespec t0, t1;
+    timespec_get(&t0, TIME_UTC);
+    do timespec_get(&t1, TIME_UTC);
+    while ((int64_t)(t1.tv_sec - t0.tv_sec) * 1000 + (t1.tv_nsec - t0.tv_nsec) / 1000000 < time_ms);
+    return EI_IMPULSE_OK;
+}
+__attribute__((weak)) uint64_t ei_read_timer_us() {
+    struct timespec ts;
+    timespec_get(&ts, TIME_UTC);
+    return (uint64_t)ts.tv_sec * 1000000ull + (uint64_t)ts.tv_nsec / 1000;
+}
+#endif
+__attribute__((weak)) EI_IMPULSE_ERROR ei_run_impulse_check_canceled() { return EI_IMPULSE_OK; }
 __attribute__((weak)) uint64_t ei_read_timer_ms() { return ei_read_timer_us() / 1000; }
 __attribute__((weak)) void ei_printf(const char *format, ...) {
     va_list ap;

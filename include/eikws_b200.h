@@ -110,7 +110,33 @@ int eikws_infer_device(eikws_handle *h, const float *d_features, size_t n_clips,
 int eikws_classify_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *probs);
 int eikws_classify_f32_host(eikws_handle *h, const float *samples, size_t n_clips, float *probs);
 int eikws_features_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *features, int8_t *qfeatures);
+int eikws_features_f32_host(eikws_handle *h, const float *samples, size_t n_clips, float *features, int8_t *qfeatures);
 int eikws_infer_host(eikws_handle *h, const float *features, size_t n_clips, float *probs);
+
+/* Thread safety: the *_host entry points and the single-clip calls below serialise on the handle (they share its staging
+ * buffers; the lock is held from the first byte staged to the last result copied); the *_device entry points only launch and
+ * may be called concurrently on different streams.  Host buffers are copied at full PCIe speed, asynchronously, only when
+ * they are page-locked: eikws_host_alloc / eikws_host_free give a pure-C host such memory without CUDA headers. */
+void *eikws_host_alloc(size_t bytes); /* NULL on failure (eikws_last_error) */
+void eikws_host_free(void *p);
+
+/* ---- several GPUs of one box behind one call ----------------------------------------------------------------
+ * The reference application classifies window after window on one core (nucleo-l476-keyword-spotting/Core/Src/main.cpp:190-194);
+ * a batch host shards its clips over the box instead.  Clips are independent: device i of D gets the contiguous range
+ * eikws_multi_shard(m, n, i, &first, &count) (sizes differ by at most one clip), one host thread and one stream pair per
+ * device, no exchange between devices; results land in place and are byte-identical to a single-device run.
+ * devices == NULL selects the first n_devices visible devices (n_devices <= 0: all of them). */
+typedef struct eikws_multi eikws_multi;
+int eikws_multi_create(const void *model_blob, size_t bytes, const int *devices, int n_devices, eikws_multi **out);
+void eikws_multi_destroy(eikws_multi *m);
+int eikws_multi_device_count(const eikws_multi *m);
+eikws_handle *eikws_multi_handle(eikws_multi *m, int i); /* the i-th device's handle (owned by m) */
+void eikws_multi_shard(const eikws_multi *m, size_t n_clips, int i, size_t *first, size_t *count);
+int eikws_multi_classify_i16_host(eikws_multi *m, const int16_t *pcm, size_t n_clips, float *probs);
+int eikws_multi_classify_f32_host(eikws_multi *m, const float *samples, size_t n_clips, float *probs);
+/* device-resident shards: d_pcm[i] / d_probs[i] live on device i of the set and hold n_clips[i] clips; asynchronous on
+ * streams[i] (streams == NULL or streams[i] == NULL: that device's default stream) */
+int eikws_multi_classify_i16_device(eikws_multi *m, const int16_t *const *d_pcm, const size_t *n_clips, float *const *d_probs, void *const *streams);
 
 /* ---- single clip through the reference's pull callback (signal_t::get_data with
  * EIDSP_SIGNAL_C_FN_POINTER=1, numpy_types.h:242-249).  Used by the drop-in run_classifier(). --- */
@@ -179,6 +205,29 @@ uint64_t eikws_launch_count(const eikws_handle *h);
 /* deterministic synthetic int16 clips written on the device (bench/test input generator);
  * clip c of the stream is generated for index first_clip + c. */
 int eikws_synth_i16_device(eikws_handle *h, int16_t *d_pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, void *stream);
+
+
+/* ---- tuning knobs (A/B measurement of kernel variants; defaults are the measured best, results never change) ---- */
+int eikws_set_ctas_per_sm(eikws_handle *h, int n);   /* clip groups resident per SM (1..8)                              */
+int eikws_set_clips_per_cta(eikws_handle *h, int n); /* clip groups per CTA: 1, 2 or 4                                   */
+int eikws_set_tensor_core(eikws_handle *h, int on);  /* block 1 of the fused classifier as a tcgen05 UMMA                */
+int eikws_set_cmvn_shortcut(eikws_handle *h, int on);/* certified CMVN shortcut (0: every chain with the exact sequence) */
+int eikws_set_work_claiming(eikws_handle *h, int on);/* work-claiming schedule of the shortcut kernel                    */
+int eikws_set_skew_ns(eikws_handle *h, int ns);      /* start offset between the CTAs that share an SM                   */
+
+/* ---- parity taps (tests only) --------------------------------------------------------------- */
+/* classify and also return the float features and the int8 classifier input */
+int eikws_classify_taps_i16_device(eikws_handle *h, const int16_t *d_pcm, size_t n_clips, float *d_probs, float *d_features,
+                                   int8_t *d_qfeatures, void *stream);
+int eikws_classify_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *probs, float *features, int8_t *qfeatures);
+/* per clip: P[129][49] power spectra, log-mel [49][33], pre-CMVN cepstra [49][13]; taps == NULL only reports the record length */
+int eikws_debug_stage_taps_i16_host(eikws_handle *h, const int16_t *pcm, size_t n_clips, float *taps, int *floats_per_clip);
+/* the CMVN + input-quantisation stage alone on caller-supplied pre-CMVN cepstra [n][49][13] -> int8 features [n][637];
+ * shortcut != 0: the certified path of the default classify kernel, 0: every chain with the reference's sequence */
+int eikws_debug_cmvn_quantise_host(eikws_handle *h, const float *cepstra, size_t n, int shortcut, int8_t *qfeatures);
+/* host-side derived tables, no GPU needed: dense mel filterbank [129][32], conv/FC requantisation multipliers and shifts */
+int eikws_debug_host_plan(const void *model_blob, size_t bytes, float *filterbank_129x32, int32_t *conv_mult, int32_t *conv_shift,
+                          int max_channels, int *n_channels);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,10 @@ int kws_model_tensor_bytes(const kws_model *m, int i);
 int kws_oracle_run_classifier_i16(const kws_model *m, const int16_t *pcm, int n, float *probs, float *features_out);
 int kws_oracle_run_classifier_f32(const kws_model *m, const float *x, int n, float *probs, float *features_out);
 
+/* the CMVN stage (processing.hpp:326-389) + input quantisation (ei_run_classifier.h:436-444) on caller-supplied pre-CMVN
+ * cepstra [frames x num_cepstral]; features_out (optional) = the float CMVN output */
+int kws_oracle_cmvn_quantise(const kws_model *m, const float *cepstra, int8_t *q, float *features_out);
+
 /* ---- continuous mode: run_classifier_continuous (ei_run_classifier.h:184-282) for ONE stream from power-up ---- */
 typedef struct kws_stream kws_stream;
 kws_stream *kws_stream_new(const kws_model *m, int slices_per_window); /* EI_CLASSIFIER_SLICES_PER_MODEL_WINDOW (4) */

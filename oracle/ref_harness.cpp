@@ -224,6 +224,15 @@ int ref_mfcc_nocmvn_i16(const int16_t *pcm, int n, float *out, int *frames) {
                                        c.num_filters, c.fft_length, c.low_frequency, c.high_frequency);
 }
 
+// The reference's own sliding-window CMVN (processing.hpp:326-389, called by extract_mfcc_features at ei_run_dsp.h:297-302)
+// on a caller-supplied [frames x num_cepstral] matrix of pre-CMVN cepstra, in place: lets the tests drive the stage with
+// matrices no audio clip produces.
+int ref_cmvnw_f32(float *m, int frames) {
+    const ei_dsp_config_mfcc_t *c = (const ei_dsp_config_mfcc_t *)ei_dsp_blocks[0].config;
+    ei::matrix_t fm(frames, c->num_cepstral, m);
+    return ei::speechpy::processing::cmvnw(&fm, c->win_size, true);
+}
+
 // One frame's magnitude spectrum via numpy::rfft (numpy.hpp:1091-1156): out[n_fft/2+1]
 #ifdef REF_HAS_MFE_BLOCK
 // The sibling DSP block of the newer SDK copy (L432): extract_mfe_features (ei_run_dsp.h:369-418) = mel filterbank energies
@@ -284,6 +293,19 @@ int ref_run_classifier_continuous_i16(const int16_t *slice, int16_t beyond, floa
 double ref_time_run_classifier_i16(const int16_t *pcm, int n, int count, float *probs_last) {
     uint64_t t0 = ei_read_timer_us();
     for (int i = 0; i < count; i++) ref_run_classifier_i16(pcm + (size_t)i * n, n, probs_last);
+    return (double)(ei_read_timer_us() - t0) * 1e-6;
+}
+
+// Same loops, but every clip's probabilities are kept ([count][labels]): bench.py compares them with the GPU's outputs
+// for the same clips, so the timed CPU baseline doubles as a parity check against the unmodified reference.
+double ref_time_run_classifier_i16_all(const int16_t *pcm, int n, int count, float *probs_all) {
+    uint64_t t0 = ei_read_timer_us();
+    for (int i = 0; i < count; i++) ref_run_classifier_i16(pcm + (size_t)i * n, n, probs_all + (size_t)i * EI_CLASSIFIER_LABEL_COUNT);
+    return (double)(ei_read_timer_us() - t0) * 1e-6;
+}
+double ref_time_run_classifier_f32_all(const float *x, int n, int count, float *probs_all) {
+    uint64_t t0 = ei_read_timer_us();
+    for (int i = 0; i < count; i++) ref_run_classifier_f32(x + (size_t)i * n, n, probs_all + (size_t)i * EI_CLASSIFIER_LABEL_COUNT);
     return (double)(ei_read_timer_us() - t0) * 1e-6;
 }
 

@@ -130,6 +130,24 @@ class RefOracle:
         assert self.lib.ref_mfcc_nocmvn_i16(_p(pcm, C.c_int16), N_SAMPLES, _p(out, C.c_float), C.byref(fr)) == 0
         return out.reshape(49, 13)
 
+    def cmvnw(self, cepstra: np.ndarray) -> np.ndarray:
+        """the reference's own processing::cmvnw on pre-CMVN cepstra [n][49][13] -> float features [n][637]"""
+        out = np.ascontiguousarray(cepstra, dtype=np.float32).reshape(-1, N_FEATURES).copy()
+        for i in range(out.shape[0]):
+            rc = self.lib.ref_cmvnw_f32(_p(out[i], C.c_float), 49)
+            assert rc == 0, rc
+        return out
+
+    def time_run_classifier_all(self, clips: np.ndarray):
+        """(seconds, probs [n][labels]) of the reference's run_classifier over int16 or float32 clips"""
+        f32 = clips.dtype == np.float32
+        clips = np.ascontiguousarray(clips, dtype=np.float32 if f32 else np.int16).reshape(-1, N_SAMPLES)
+        out = np.zeros((clips.shape[0], self.n_labels), np.float32)
+        fn = self.lib.ref_time_run_classifier_f32_all if f32 else self.lib.ref_time_run_classifier_i16_all
+        fn.restype = C.c_double
+        t = float(fn(_p(clips, C.c_float if f32 else C.c_int16), N_SAMPLES, clips.shape[0], _p(out, C.c_float)))
+        return t, out
+
     def time_run_classifier_i16(self, pcm: np.ndarray) -> float:
         pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, N_SAMPLES)
         last = np.zeros(self.n_labels, np.float32)
@@ -226,6 +244,17 @@ class PortOracle:
                 rc = self.lib.kws_oracle_run_inference(self.m, _p(features[i], C.c_float), _p(probs[i], C.c_float), None)
             assert rc == 0, rc
         return (probs, all_t) if want_tensors else probs
+
+    def cmvn_quantise(self, cepstra: np.ndarray, want_features=False):
+        """CMVN + int8 input quantisation of pre-CMVN cepstra [n][49][13] -> int8 [n][637] (and the float features)"""
+        cep = np.ascontiguousarray(cepstra, dtype=np.float32).reshape(-1, self.n_features)
+        q = np.zeros(cep.shape, np.int8)
+        f = np.zeros(cep.shape, np.float32)
+        self.lib.kws_oracle_cmvn_quantise.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int8), C.POINTER(C.c_float)]
+        for i in range(cep.shape[0]):
+            rc = self.lib.kws_oracle_cmvn_quantise(self.m, _p(cep[i], C.c_float), _p(q[i], C.c_int8), _p(f[i], C.c_float))
+            assert rc == 0, rc
+        return (q, f) if want_features else q
 
     def run_classifier_i16(self, pcm: np.ndarray, want_features=False):
         pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1, N_SAMPLES)

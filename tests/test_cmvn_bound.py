@@ -176,24 +176,12 @@ def test_emulation_is_the_oracle(synth):
 def test_bound_on_adversarial_matrices():
     """cepstra matrices no audio clip produces: huge mean/sigma ratios, near-constant columns, outliers, tiny and huge magnitudes,
     exact ties.  A certified decision must always equal the emulated reference's; the bound must hold with room."""
-    rng = np.random.default_rng(20261017)
+    import cmvn_cases
     scale, zp = np.float32(0.046360891312360764), -11
     inv_scale = np.float32(1.0 / float(scale))
     src = pad_rows()
-    mats = []
-    for sigma in (1e-3, 1.0, 30.0, 1e3):
-        for ratio in (0.0, 10.0, 1e3, 1e5, -1e4):
-            mats.append((rng.standard_normal((49, 13)) * sigma + ratio * sigma).astype(np.float32))
-    for k in range(10):
-        m = (rng.standard_normal((49, 13)) * 3).astype(np.float32)
-        m[rng.integers(0, 49), :] += np.float32(10.0 ** rng.integers(1, 6))      # one outlier frame
-        mats.append(m)
-        mats.append((np.float32(7.25) + rng.standard_normal((49, 13)) * 1e-6).astype(np.float32))  # nearly constant
-        mats.append((rng.standard_normal((49, 13)) * 10.0 ** rng.integers(-20, 15)).astype(np.float32))
-        mats.append(np.where(rng.random((49, 13)) < 0.5, np.float32(1.0), np.float32(-1.0)).astype(np.float32) * np.float32(2.5))
-        mats.append(np.round(rng.standard_normal((49, 13)) * 4).astype(np.float32) * scale)  # many exact-looking values
-    mats.append(np.zeros((49, 13), np.float32))
-    mats.append(np.full((49, 13), 3.0, np.float32))
+    mats = cmvn_cases.adversarial_matrices(scale)  # the GPU test feeds the same 72 matrices to the device code
+    assert len(mats) == 72
     worst, certified, total = 0.0, 0, 0
     for mi, F32 in enumerate(mats):
         f_ref = reference_cmvn_f32(F32)
@@ -229,3 +217,29 @@ def test_bound_on_adversarial_matrices():
             worst = max(worst, float(r2.max()))
     assert worst < 0.6, f"reference within {worst:.2f} B of the bound"
     assert certified > 0.3 * total  # the guard conditions must not simply refuse everything
+
+
+def test_cmvn_stage_of_the_port_is_the_reference_on_matrices_no_clip_produces():
+    """pins PortOracle.cmvn_quantise -- the CPU side of the GPU test of the device shortcut -- to the UNMODIFIED reference's own
+    processing::cmvnw (oracle/_ref) on the adversarial, special-value and near-boundary matrices themselves"""
+    import cmvn_cases
+    from oracle_lib import RefOracle, have_ref
+    if not have_ref("l476"):
+        pytest.skip("oracle/_ref not built")
+    scale = np.float32(0.046360891312360764)
+    mats = np.stack(cmvn_cases.adversarial_matrices(scale) + cmvn_cases.special_value_matrices() +
+                    list(cmvn_cases.near_boundary_matrices(64, scale, seed=5)[0]))
+    with np.errstate(all="ignore"):
+        _, f_port = PortOracle("l476").cmvn_quantise(mats, want_features=True)
+        f_ref = RefOracle("l476").cmvnw(mats)
+    assert np.array_equal(f_port.view(np.uint32), f_ref.view(np.uint32)) or np.all((f_port == f_ref) | (np.isnan(f_port) & np.isnan(f_ref)))
+
+
+def test_near_boundary_generator_lands_near_boundaries():
+    import cmvn_cases
+    scale = np.float32(0.046360891312360764)
+    F, r = cmvn_cases.near_boundary_matrices(256, scale, seed=11)
+    _, f = PortOracle("l476").cmvn_quantise(F, want_features=True)
+    t = (f.reshape(-1, 49, 13) / scale)[np.arange(256)[:, None], r, np.arange(13)[None, :]].astype(np.float64)
+    dist = np.abs(t - np.floor(t) - 0.5)
+    assert np.median(dist) < 1e-3 and (dist < 1e-5).mean() > 0.1  # targeted chains sit on the boundary at rounding-error scale

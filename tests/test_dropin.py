@@ -79,3 +79,52 @@ def test_dropin_run_classifier_continuous_matches_oracle(tag, tmp_path, synth):
         assert (want is None) == (i not in got)
         if want is not None:
             assert np.allclose(got[i], want, atol=1e-8)
+
+
+def test_c_hosts_compile_as_c11(tmp_path):
+    """a pure-C translation unit (gcc -std=c11, -Wall -Werror) gets run_classifier & co. from the drop-in header; the C++ shim
+    ei_run_classifier_c.cpp defines them with C linkage (the reference's README has users delete its C wrapper, README.md:185)"""
+    ref = "/root/reference/embedded-demos/stm32cubeide/nucleo-l432-keyword-spotting/keyword-spotting-02-v3"
+    if not os.path.isdir(ref):
+        pytest.skip("needs the reference export to compile against")
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + ref]
+    for ex in ("static_buffer", "batch_multi_gpu"):
+        subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", *inc, "-c", os.path.join(ROOT, "examples", ex + ".c"), "-o", str(tmp_path / (ex + ".o"))], check=True)
+    shim = os.path.join(ROOT, "include", "edge-impulse-sdk", "classifier", "ei_run_classifier_c.cpp")
+    subprocess.run(["g++", "-std=gnu++14", "-w", *inc, "-c", shim, "-o", str(tmp_path / "shim.o")], check=True)
+    syms = subprocess.run(["nm", "--defined-only", str(tmp_path / "shim.o")], capture_output=True, text=True, check=True).stdout
+    for s in ("run_classifier", "run_classifier_continuous", "run_classifier_init", "run_classifier_batch_i16", "run_classifier_batch_f32",
+              "ei_b200_init", "ei_b200_shutdown"):
+        assert re.search(rf" T {s}$", syms, flags=re.M), f"{s} is not defined with C linkage by the shim"
+    # the shim's copy of the generated globals is internal: the application's .c file owns the external ones
+    assert not re.search(r" [DB] ei_classifier_inferencing_categories$", syms, flags=re.M)
+
+
+@pytest.mark.parametrize("tag", ["l476", "l432"])
+def test_c_host_fails_loudly_without_gpu(tag):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([_binary(tag, "static_buffer_c")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "run_classifier returned -6" in r.stdout and "no usable CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["l476", "l432"])
+def test_c_host_run_classifier_matches_oracle(tag, tmp_path, synth):
+    clip = synth.synth_clips(1, first_clip=79)[0]
+    f = tmp_path / "clip.pcm"
+    clip.tofile(f)
+    r = subprocess.run([_binary(tag, "static_buffer_c"), str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = [float(v) for v in re.findall(r":\s+([0-9.]+)\s*$", r.stdout, flags=re.M)]
+    port = PortOracle(tag)
+    assert re.findall(r"^\s+(\S+): [0-9.]+\s*$", r.stdout, flags=re.M) == port.labels
+    assert np.allclose(got, port.run_classifier_i16(clip)[0], atol=5e-6)
+
+
+@pytest.mark.gpu
+def test_c_batch_host_shards_over_every_gpu():
+    """examples/batch_multi_gpu.c: ei_b200_init(all devices) + run_classifier_batch_i16 == the same batch on one device"""
+    r = subprocess.run([_binary("l476", "batch_multi_gpu_c"), "3001", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sharded == single device" in r.stdout, r.stdout + r.stderr

@@ -140,3 +140,117 @@ def test_tuning_knobs_are_exported_and_validate_their_arguments(eikws):
         fn.argtypes = [C.c_void_p, C.c_int]
         fn.restype = C.c_int
         assert fn(None, 1) != 0
+
+
+def _mutations(blob: bytes):
+    """(description, mutated container) pairs: every one must be refused by parse/validate or by the lowering -- never crash.
+    Layout (include/eikws_model_format.md): magic(8) version n_tensors n_nodes input output n_labels raw n_features, then the
+    11 MFCC fields, labels, tensors, nodes."""
+    import struct
+    out = []
+
+    def put(off, fmt, v, what):
+        b = bytearray(blob)
+        struct.pack_into(fmt, b, off, v)
+        out.append((what, bytes(b)))
+
+    hdr = 8 + 4 * 8
+    put(hdr + 4 * 8, "<i", 40000, "high_frequency above Nyquist (mel_filterbank used to write past its 129-row table)")
+    put(hdr + 4 * 8, "<i", 100, "high_frequency below low_frequency")
+    put(hdr + 4 * 7, "<i", -5, "negative low_frequency")
+    put(hdr + 4 * 0, "<i", 0, "sample rate 0")
+    put(8 + 4 * 3, "<I", 4000, "input tensor index out of range")
+    put(8 + 4 * 1, "<I", 5000, "implausible tensor count")
+    # walk the container to reach the tensors and nodes
+    off = hdr + 4 * 11
+    n_t, n_n, _, _, n_l = struct.unpack_from("<5I", blob, 12)
+    for _ in range(n_l):
+        (ln,) = struct.unpack_from("<I", blob, off)
+        off += 4 + ((ln + 3) & ~3)
+    tens = []
+    for _ in range(n_t):
+        t0 = off
+        ttype, is_const, nd = struct.unpack_from("<3I", blob, off)
+        off += 12 + 4 * nd
+        (nbytes,) = struct.unpack_from("<I", blob, off)
+        bytes_off = off
+        (nq,) = struct.unpack_from("<I", blob, off + 4)
+        scales_off = off + 8
+        off += 8 + 8 * nq + 4
+        if is_const:
+            off += (nbytes + 3) & ~3
+        tens.append(dict(start=t0, type=ttype, is_const=is_const, nd=nd, bytes_off=bytes_off, nq=nq, scales_off=scales_off))
+    nodes = []
+    for _ in range(n_n):
+        n0 = off
+        op, n_in = struct.unpack_from("<2I", blob, off)
+        in_off = off + 8
+        off = in_off + 4 * n_in
+        (n_out,) = struct.unpack_from("<I", blob, off)
+        out_off = off + 4
+        off = out_off + 4 * n_out
+        (n_par,) = struct.unpack_from("<I", blob, off)
+        par_cnt_off = off
+        off += 4 + 4 * n_par
+        nodes.append(dict(start=n0, op=op, n_in=n_in, in_off=in_off, n_out=n_out, out_off=out_off, n_par=n_par, par_cnt_off=par_cnt_off))
+    assert off == len(blob), "container walked to its end"
+    conv = next(n for n in nodes if n["op"] == 3)
+    # a CONV_2D with no parameters: the parameter words are cut out of the container
+    b = bytearray(blob)
+    struct.pack_into("<I", b, conv["par_cnt_off"], 0)
+    del b[conv["par_cnt_off"] + 4: conv["par_cnt_off"] + 4 + 4 * conv["n_par"]]
+    out.append(("CONV_2D with n_params = 0 (the lowering used to index params[4])", bytes(b)))
+    put(conv["in_off"], "<i", -1, "CONV_2D whose input tensor is -1")
+    put(conv["in_off"] + 4, "<i", -1, "CONV_2D whose filter tensor is -1")
+    put(conv["out_off"], "<i", n_t + 3, "node output index out of range")
+    put(conv["par_cnt_off"] + 4 + 4 * 1, "<i", 0, "CONV_2D stride 0")
+    pool = next(n for n in nodes if n["op"] == 17)
+    put(pool["par_cnt_off"] + 4 + 4 * 2, "<i", 0, "MAX_POOL_2D stride 0")
+    act = next(t for t in tens if not t["is_const"] and t["nd"] > 0)
+    put(act["start"] + 12, "<i", 0, "activation tensor with a zero dimension")
+    put(act["bytes_off"], "<I", 7, "activation tensor whose byte size contradicts its shape")
+    qt = next((t for t in tens if t["nq"] >= 1), None)  # (the float32 graph carries no quantisation parameters)
+    if qt:
+        put(qt["scales_off"], "<f", 0.0, "zero quantisation scale")
+        put(qt["scales_off"], "<f", float("nan"), "NaN quantisation scale")
+    cst = next(t for t in tens if t["is_const"] and t["type"] in (9, 1) and t["nd"] == 4)
+    put(cst["start"] + 12, "<i", 60, "filter whose shape disagrees with its data size")
+    put(cst["start"], "<I", 77, "unknown element type")
+    out.append(("truncated in the middle of the node table", blob[: nodes[len(nodes) // 2]["start"] + 6]))
+    return out
+
+
+@pytest.mark.parametrize("name", ["l476", "l476f32", "dw3", "zip6"])
+def test_mutated_containers_are_refused_not_crashed_on(eikws, name):
+    """the container is untrusted input of two public entry points (eikws_create, eikws_debug_host_plan): structural damage must
+    come back as an error code from parse_model / validate_model / the lowering, never as an out-of-bounds access (this test runs
+    the lowering on every mutation; under ASan/valgrind it is the regression test of the findings in ADVICE.md)"""
+    lib = eikws.load_library()
+    blob = eikws.model_blob(name)
+    n = C.c_int(0)
+    assert lib.eikws_debug_host_plan(blob, len(blob), None, None, None, 0, C.byref(n)) == 0
+    muts = _mutations(blob)
+    assert len(muts) >= 17
+    for what, bad in muts:
+        rc = lib.eikws_debug_host_plan(bad, len(bad), None, None, None, 0, C.byref(n))
+        assert rc in (-102, -100, -1), f"{name}: {what}: rc {rc}"
+        assert lib.eikws_last_error(), what
+    # random single-word damage anywhere behind the header: any outcome but a crash is acceptable
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        b = bytearray(blob)
+        off = int(rng.integers(12, len(b) - 4))
+        b[off:off + 4] = int(rng.choice([0, 0xFFFFFFFF, 0x7FFFFFFF, 0x80000000, 1 << 20, int(rng.integers(0, 1 << 32))])).to_bytes(4, "little")
+        lib.eikws_debug_host_plan(bytes(b), len(b), None, None, None, 0, C.byref(n))
+
+
+def test_multi_device_api_without_gpu_fails_loudly(eikws):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(eikws.EikwsError) as ei:
+        eikws.MultiImpulse("l476")
+    assert ei.value.code == -101
+    lib = eikws.load_library()
+    assert lib.eikws_multi_device_count(None) == 0 and lib.eikws_multi_handle(None, 0) is None
+    assert lib.eikws_host_alloc(64) is None and b"cudaHostAlloc" in lib.eikws_last_error()
