@@ -370,3 +370,131 @@ def test_certified_cmvn_shortcut_is_bit_identical(name, impulses, synth):
         imp.set_cmvn_shortcut(True)
         imp.set_tensor_core(True)
         imp.set_clips_per_cta(2)
+
+
+@pytest.mark.parametrize("name", ["l476", "gsc12"])
+def test_device_cmvn_shortcut_on_adversarial_cepstra(name, impulses):
+    """The DEVICE implementation of the certified CMVN shortcut (cmvn_certified / cmvn_resolve, MUFU sqrt.approx / rcp.approx
+    inside) fed directly with pre-CMVN cepstra through eikws_debug_cmvn_quantise_host -- matrices no audio clip produces:
+    the 72 hand-shaped adversarial matrices of test_cmvn_bound.py, denormal / huge / inf / NaN columns, and > 10^6 random
+    matrices in which one frame per column was moved ONTO a rounding boundary k + 1/2 of the int8 quantisation (to within the
+    reference's own rounding errors: the only place where a nearly-right shortcut flips a bit).  Bar: byte equality with the
+    every-chain kernel on all of them, and with the CPU oracle's CMVN (pinned to the unmodified reference's cmvnw on these very
+    matrix families, test_cmvn_bound.py) on every hand-shaped matrix and a 12,288-matrix subset.
+    reference: processing.hpp:326-389, numpy.hpp:767-825, ei_run_classifier.h:436-444"""
+    import cmvn_cases
+    imp = impulses[name]
+    port = PortOracle(name)
+    scale = {"l476": 0.046360891312360764}.get(name)
+    if scale is None:  # the input scale of the model, from its container (tensor 0 of the int8 graph is the input)
+        _, t0 = port.run_inference(np.zeros((1, 637), np.float32), want_tensors=True)
+        zp = int(t0[0][0].view(np.int8)[0])
+        probe = np.zeros((1, 637), np.float32)
+        lo, hi = 0.0, 64.0
+        for _ in range(60):  # f with round(f / scale) == 40 |-> bisect the 39.5 boundary
+            mid = 0.5 * (lo + hi)
+            probe[0, 0] = mid
+            _, t = port.run_inference(probe, want_tensors=True)
+            if int(t[0][0].view(np.int8)[0]) - zp >= 40:
+                hi = mid
+            else:
+                lo = mid
+        scale = hi / 39.5
+    hand = np.stack(cmvn_cases.adversarial_matrices(scale) + cmvn_cases.special_value_matrices())
+    with np.errstate(all="ignore"):
+        want = port.cmvn_quantise(hand)
+    q_short = imp.debug_cmvn_quantise(hand, shortcut=True)
+    q_exact = imp.debug_cmvn_quantise(hand, shortcut=False)
+    for i in range(len(hand)):
+        assert np.array_equal(q_exact[i], want[i]), f"hand-shaped matrix {i}: every-chain kernel differs from the oracle"
+        assert np.array_equal(q_short[i], want[i]), f"hand-shaped matrix {i}: certified shortcut differs from the oracle"
+    total = checked_cpu = near = 0
+    chunk = 65536
+    for c in range(16 if name == "l476" else 2):  # 1,048,576 matrices (13.6 M targeted chains) for the headline model
+        F, r = cmvn_cases.near_boundary_matrices(chunk, scale, seed=1000 + c)
+        qs = imp.debug_cmvn_quantise(F, shortcut=True)
+        qe = imp.debug_cmvn_quantise(F, shortcut=False)
+        bad = np.nonzero((qs != qe).any(axis=1))[0]
+        assert bad.size == 0, f"chunk {c}: shortcut and every-chain kernels disagree on matrices {bad[:8].tolist()}"
+        sub = slice(0, 768)
+        with np.errstate(all="ignore"):
+            w, f = port.cmvn_quantise(F[sub], want_features=True)
+        assert np.array_equal(qs[sub], w), f"chunk {c}: shortcut differs from the CPU oracle"
+        t = (f.reshape(-1, 49, 13) / np.float32(scale))[np.arange(768)[:, None], r[sub], np.arange(13)[None, :]].astype(np.float64)
+        near += int((np.abs(t - np.floor(t) - 0.5) < 1e-4).sum())
+        checked_cpu += 768
+        total += chunk
+    assert total >= (1 << 20 if name == "l476" else 1 << 17) and checked_cpu >= (12288 if name == "l476" else 1536)
+    assert near > 0.3 * checked_cpu * 13  # the targeted chains really sit at the boundaries
+
+
+def test_multi_device_host_api_equals_one_device(eikws, impulses, synth):
+    """eikws_multi_*: contiguous shards over every visible GPU, one host thread + stream pair per device, results in place ==
+    the single-device result, byte for byte (ragged batch sizes included).  With one visible GPU the set has one device and the
+    test still covers the thread/shard plumbing; the 2-, 4-, 8-way split runs where the box has the GPUs."""
+    import torch
+    multi = eikws.MultiImpulse("l476")
+    try:
+        assert multi.device_count == torch.cuda.device_count()
+        for n in (1, 7, 4097, 20000):
+            clips = synth.synth_clips(min(n, 512), first_clip=555)
+            clips = np.resize(clips, (n, 16000)) if n > 512 else clips[:n]
+            want = impulses["l476"].run_classifier(clips)
+            got = multi.run_classifier(clips)
+            assert np.array_equal(got, want), f"n={n}"
+            covered = sum(multi.shard(n, i)[1] for i in range(multi.device_count))
+            assert covered == n and multi.shard(n, 0)[0] == 0
+        # the same through float samples
+        x = synth.synth_clips(33, first_clip=9).astype(np.float32) / np.float32(32768)
+        assert np.array_equal(multi.run_classifier(x), impulses["l476"].run_classifier(x))
+    finally:
+        multi.close()
+    if torch.cuda.device_count() >= 2:  # an explicit device list, in reverse order
+        m2 = eikws.MultiImpulse("l476", devices=[1, 0])
+        try:
+            clips = synth.synth_clips(301, first_clip=1234)
+            assert np.array_equal(m2.run_classifier(clips), impulses["l476"].run_classifier(clips))
+        finally:
+            m2.close()
+    lib = eikws.load_library()
+    h = C.c_void_p()
+    blob = eikws.model_blob("l476")
+    arr = (C.c_int * 2)(0, 0)
+    assert lib.eikws_multi_create(blob, len(blob), arr, 2, C.byref(h)) == -102  # a device listed twice
+    arr = (C.c_int * 1)(99)
+    assert lib.eikws_multi_create(blob, len(blob), arr, 1, C.byref(h)) == -102  # no such device
+
+
+def test_single_clip_calls_from_many_threads_do_not_mix_clips(eikws, impulses, synth):
+    """eikws_run_classifier_signal holds the handle's lock from the callback's first write into the shared pinned staging buffer
+    to the last result byte: 8 threads x 40 calls, each thread with its own clip, every result must be its own clip's"""
+    import threading
+    lib = eikws.load_library()
+    imp = impulses["l476"]
+    clips = synth.synth_clips(8, first_clip=31)
+    want = imp.run_classifier(clips)
+    CB = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_float))
+    lib.eikws_run_classifier_signal.argtypes = [C.c_void_p, CB, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    errors = []
+
+    def worker(k):
+        x = clips[k].astype(np.float32) / np.float32(32768)
+
+        def get_data(off, length, out):
+            C.memmove(out, x[off:off + length].ctypes.data, 4 * length)
+            return 0
+
+        cb = CB(get_data)
+        vals = (C.c_float * imp.label_count)()
+        for _ in range(40):
+            rc = lib.eikws_run_classifier_signal(imp._h, cb, 16000, vals, None, None)
+            if rc != 0 or not np.array_equal(np.frombuffer(vals, np.float32), want[k]):
+                errors.append((k, rc))
+                return
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
