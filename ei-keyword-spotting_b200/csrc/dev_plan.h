@@ -96,6 +96,7 @@ struct NnFusedStage {
 
 struct NnFusedDev {
     int32_t enabled;
+    int32_t shape;  // 0: conv 1x7 + pool 7, second block pooled by the tail (STM32 exports); 1: conv 1x3 + pool 2 (SAME), twice (Arduino zip)
     NnFusedStage st[2];
     // tail: FULLY_CONNECTED [fc_d] -> [fc_o], SOFTMAX over fc_o
     int32_t fc_in_off, fc_d, fc_o, fc_in_zp, fc_out_zp, fc_act_min, fc_act_max, fc_mult, fc_shift;

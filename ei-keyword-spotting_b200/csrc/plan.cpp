@@ -817,16 +817,25 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             arena += (bytes + 15) & ~15;
             return o;
         };
+        // two stage shapes are implemented (kernels.cu, fused_stage0 / fused_stage1): the shipped STM32 topology -- conv 1x7, pool 7
+        // (fu.shape 0; its tiny second block leaves the pool to the tail warp) -- and the Arduino-zip topology -- conv 1x3, pool 2
+        // with SAME padding, i.e. a partial last window (fu.shape 1; FC over pool_out x out_c inputs)
+        int shape = -1;
         for (int s2 = 0; ok && s2 < 2; s2++) {
             const NnOpDev &cv = nn.ops[3 * s2], &ad = nn.ops[3 * s2 + 1], &pl = nn.ops[3 * s2 + 2];
             const ConvSrc *cs = find_conv(3 * s2);
             const std::vector<uint8_t> *lut = find_lut(3 * s2 + 1);
             NnFusedStage &st = fu.st[s2];
             const int cp = (cv.in_c + 15) & ~15;
-            // the pool must run along the conv width (tensor reshaped to [1, W, 1, C]) with window == stride, no padding
-            ok = cs && lut && cv.stride_w == 1 && cv.kw == 7 && cp == (s2 == 0 ? 16 : 32) && cv.out_w == cv.in_w && ad.n_const == cv.out_c &&
-                 ad.n_elems == cv.out_w * cv.out_c && pl.in_w == 1 && pl.kw == 1 && pl.in_h == cv.out_w && pl.in_c == cv.out_c && pl.kh == 7 &&
-                 pl.stride_h == 7 && pl.pad_h == 0 && pl.out_h * 7 == pl.in_h && pl.out_w == 1;
+            // the pool must run along the conv width (tensor reshaped to [1, W, 1, C]) with window == stride and no leading padding
+            ok = cs && lut && cv.stride_w == 1 && cv.out_w == cv.in_w && ad.n_const == cv.out_c && ad.n_elems == cv.out_w * cv.out_c &&
+                 pl.in_w == 1 && pl.kw == 1 && pl.in_h == cv.out_w && pl.in_c == cv.out_c && pl.pad_h == 0 && pl.out_w == 1 && pl.kh == pl.stride_h;
+            if (!ok) break;
+            const bool shape_a = cv.kw == 7 && pl.kh == 7 && pl.out_h * 7 == pl.in_h && cp == (s2 == 0 ? 16 : 32);
+            const bool shape_b = cv.kw == 3 && pl.kh == 2 && pl.out_h == (pl.in_h + 1) / 2 && cp == 16;
+            const int this_shape = shape_a ? 0 : (shape_b ? 1 : -1);
+            if (s2 == 0) shape = this_shape;
+            ok = this_shape >= 0 && this_shape == shape;
             if (s2 == 0) ok = ok && cv.in_w == kFrames && cv.in_c == kCepstra;
             if (!ok) break;
             st.in_w = cv.in_w;
@@ -837,7 +846,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
             st.out_c = cv.out_c;
             st.pool = pl.kh;
             st.pool_out = pl.out_h;
-            if (s2 == 1) {
+            if (s2 == 1 && shape == 0) {
                 // the second block is tiny (7 x 10 outputs): one thread per conv output, the max-pool moves to the tail warp
                 ok = pl.out_h == 1;
                 st.pool = 1;
@@ -845,14 +854,21 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 fu.tail_pool = pl.kh;
                 fu.tail_pool_act_min = pl.act_min;
                 fu.tail_pool_act_max = pl.act_max;
+            } else if (s2 == 1) {
+                fu.tail_pool = 1;  // pooled inside the stage
+                fu.tail_pool_act_min = -128;
+                fu.tail_pool_act_max = 127;
             }
             st.in_zp = cv.in_zp;
             st.conv_out_zp = cv.out_zp;
             st.conv_act_min = cv.act_min;
             st.conv_act_max = cv.act_max;
-            st.pool_act_min = s2 == 1 ? -128 : pl.act_min;
-            st.pool_act_max = s2 == 1 ? 127 : pl.act_max;
-            st.in_rows = cv.in_w + cv.kw - 1;
+            const bool pool_in_tail = s2 == 1 && shape == 0;
+            st.pool_act_min = pool_in_tail ? -128 : pl.act_min;
+            st.pool_act_max = pool_in_tail ? 127 : pl.act_max;
+            // padded input rows: the image plus the conv halo, and every row the LAST pool group's window touches (a partial window
+            // still reads its full POOL + KW - 1 rows; the outputs beyond the image are dropped, not their reads)
+            st.in_rows = std::max(cv.in_w + cv.kw - 1, st.pool_out * st.pool + cv.kw - 1);
             // the fused stage pools the ACCUMULATORS (max commutes with monotone steps): needs non-negative multipliers
             // and a non-decreasing ADD+activation table for every channel
             for (int oc = 0; ok && oc < cv.out_c; oc++) {
@@ -881,15 +897,19 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
         if (ok) {
             const NnOpDev &fc = nn.ops[6], &sm = nn.ops[7];
             const ConvSrc *cs = find_conv(6);
-            ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fu.st[1].out_c && fu.st[1].pool_out == fu.tail_pool && fu.st[1].in_w == fu.st[0].pool_out &&
-                 fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && fc.in_c <= 32 && fu.st[0].in_rows * fu.st[0].cp <= 1024 &&
-                 fu.st[1].in_rows * fu.st[1].cp <= 512 && fc.in_c * fu.tail_pool <= 256 &&  // region S of the kernel's shared memory map
-                 sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
+            // FC input = block 2's output: [tail_pool positions][out_c] still to be pooled by the tail (shape 0) or the pooled
+            // [pool_out][out_c] matrix (shape 1)
+            const int fc_in = shape == 0 ? fu.st[1].out_c : fu.st[1].pool_out * fu.st[1].out_c;
+            const int blk2_bytes = shape == 0 ? fc.in_c * fu.tail_pool : fc_in;
+            ok = cs && fc.in_w == 1 && fc.kw == 1 && fc.in_c == fc_in && (shape != 0 || fu.st[1].pool_out == fu.tail_pool) &&
+                 fu.st[1].in_w == fu.st[0].pool_out && fu.st[1].in_c == fu.st[0].out_c && fc.out_c <= 32 && (shape != 0 || fc.in_c <= 32) &&
+                 fu.st[0].in_rows * fu.st[0].cp <= 1024 && fu.st[1].in_rows * fu.st[1].cp <= 512 && blk2_bytes <= 256 &&  // region S of the kernel's shared memory map
+                 fu.st[0].out_c <= 32 && fu.st[1].out_c <= 32 && sm.n_elems == fc.out_c && fc.out_c == static_cast<int>(g.labels.size());
             if (ok) {
                 NnFusedStage &s0 = fu.st[0], &s1 = fu.st[1];
                 s0.in_off = alloc(s0.in_rows * s0.cp);
                 s1.in_off = alloc(s1.in_rows * s1.cp);
-                fu.fc_in_off = alloc(fc.in_c * fu.tail_pool);  // [tail_pool positions][fc_d] conv+add outputs of block 2
+                fu.fc_in_off = alloc(blk2_bytes);  // block 2's output
                 fu.tail_off = alloc(64);
                 s0.out_off = s1.in_off;  // stage 0 writes stage 1's padded input
                 s0.out_cp = s1.cp;
@@ -897,9 +917,9 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 s0.out_rows = s1.in_rows;
                 s0.out_fill = s1.in_zp;
                 s1.out_off = fu.fc_in_off;  // stage 1 writes the dense FC input
-                s1.out_cp = fc.in_c;
+                s1.out_cp = s1.out_c;
                 s1.out_row0 = 0;
-                s1.out_rows = fu.tail_pool;
+                s1.out_rows = s1.pool_out;
                 s1.out_fill = 0;
                 fu.fc_d = fc.in_c;
                 fu.fc_o = fc.out_c;
@@ -919,6 +939,7 @@ int build_host_plan(const ModelGraph &g, HostPlan &hp, std::string &err) {
                 b.bind(fu.fc_bias, b.push(fbias.data(), fbias.size() * 4));
                 b.bind(fu.exp_lut, b.push(exp_lut_src.data(), exp_lut_src.size() * 4));
                 fu.enabled = 1;
+                fu.shape = shape;
                 // A operand of the tensor-core block 1 (dev_plan.h): needs the shipped stage-0 shape (7 taps of one 16-byte row)
                 if (s0.kw == 7 && s0.cp == 16 && s0.out_c <= 30 && s0.in_w == kFrames && s0.pool == 7 && s0.pool_out == 7 && s0.pad_w == 3) {
                     const ConvSrc *c0 = find_conv(0);

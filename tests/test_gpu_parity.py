@@ -236,7 +236,7 @@ def test_error_behaviour(eikws, impulses):
     assert np.array_equal(np.array(vals[:], np.float32), g["probs"][sil])
 
 
-@pytest.mark.parametrize("name", ["l476", "l432", "gsc12"])
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "zip6"])
 def test_continuous_mode_matches_oracle(name, eikws, impulses, synth):
     """run_classifier_continuous for 37 concurrent streams x 14 slices against the plain-C oracle, stream by stream"""
     from oracle_lib import PortStream
@@ -306,7 +306,7 @@ def test_tensor_core_block1_is_bit_identical(name, impulses, synth):
         imp.set_tensor_core(True)  # the default
 
 
-@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3"])
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3", "zip6"])
 def test_certified_cmvn_shortcut_is_bit_identical(name, impulses, synth):
     """The default classify kernel decides round(f / scale) of most CMVN outputs from double-precision window statistics plus
     a rigorous error bound and runs the reference's operation sequence only for the chains the bound cannot certify
