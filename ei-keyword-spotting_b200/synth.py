@@ -81,3 +81,56 @@ def special_clips() -> dict:
     burst[4000:4400] = synth_clips(1, first_clip=7)[0][:400].astype(np.int64) * 3
     d["burst"] = np.clip(burst, -32768, 32767).astype(np.int16)
     return d
+
+
+# ---- speech-like clips (integer arithmetic only: reproducible bit for bit on any machine) ------------------------------
+def _isin(phase: np.ndarray) -> np.ndarray:
+    """integer sine: phase in 1/65536 turns -> [-32767, 32767] (parabola + one refinement step, all int64)"""
+    x = phase.astype(np.int64) & 0xFFFF
+    x = np.where(x >= 32768, x - 65536, x)
+    y = (x * (32768 - np.abs(x))) >> 13
+    y = y + ((((y * np.abs(y)) >> 15) - y) * 7373 >> 15)
+    return np.clip(y, -32767, 32767)
+
+
+def speechlike_clip(params) -> np.ndarray:
+    """One voiced-word-like clip from 10 small integers: a harmonic stack on a gliding pitch, weighted by three formant peaks that
+    move from one vowel to another, under a syllable envelope, with a noise burst (a 'consonant') in front and light background
+    noise -- closer to what the classifiers were trained on than Gaussian noise, so every label gets to win (tests/golden).
+    params = (f0_hz, glide_hz, vowel_a, vowel_b, onset_ms, length_ms, level, burst_ms, burst_level, seed)"""
+    f0, glide, va, vb, onset_ms, length_ms, level, burst_ms, burst_level, seed = (int(v) for v in params)
+    vowels = ((730, 1090, 2440), (270, 2290, 3010), (300, 870, 2240), (530, 1840, 2480), (660, 1720, 2410), (440, 1020, 2240),
+              (490, 1350, 1690), (640, 1190, 2390))  # Peterson-Barney style (F1, F2, F3) in Hz
+    n = np.arange(N_SAMPLES, dtype=np.int64)
+    on, ln = onset_ms * 16, max(1, length_ms * 16)
+    t = np.clip(n - on, 0, ln)  # position inside the syllable
+    # pitch glides linearly over the syllable; phase = cumulative sum of the per-sample increment (1/65536 turns)
+    f_inst = f0 * ln + glide * t  # Hz * ln
+    inc = (f_inst * 65536) // (16000 * ln)
+    phase = np.cumsum(inc)
+    fa, fb = vowels[va % 8], vowels[vb % 8]
+    voiced = np.zeros(N_SAMPLES, np.int64)
+    for h in range(1, 24):
+        fh = h * (f0 + glide // 2)
+        if fh > 3800:
+            break
+        w = 0
+        for k in range(3):  # formant k moves from vowel a to vowel b; triangular resonance of half-width 220 Hz, later ones weaker
+            # weight evaluated at the syllable midpoint (constant per harmonic keeps everything integer and cheap)
+            fc = (fa[k] + fb[k]) // 2
+            w += max(0, 220 - abs(fh - fc)) * (4 - k)
+        w = max(w, 12)
+        voiced += (w * _isin(phase * h)) >> 7
+    env = (_isin((t * 32768) // ln) * level) >> 15  # half-sine syllable envelope, 0 outside
+    env = np.where((n >= on) & (n < on + ln), env, 0)
+    x = (voiced * env) >> 15
+    r = _splitmix64((np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + n.astype(np.uint64)) & _M64)
+    noise = ((r & np.uint64(0xFFFF)).astype(np.int64) + ((r >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64)) - 65535
+    b0, b1 = max(0, on - burst_ms * 16), on
+    x = x + np.where((n >= b0) & (n < b1), (noise * burst_level) >> 12, 0) + ((noise * 3) >> 10)
+    return np.clip(x, -32768, 32767).astype(np.int16)
+
+
+def speechlike_clips(param_rows) -> np.ndarray:
+    rows = np.asarray(param_rows).reshape(-1, 10)
+    return np.stack([speechlike_clip(r) for r in rows]) if len(rows) else np.zeros((0, N_SAMPLES), np.int16)

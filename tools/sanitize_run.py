@@ -44,7 +44,7 @@ for name in (("l476", "zip6") if quick else ("l476", "l432", "gsc12", "dw3", "zi
     assert torch.equal(torch.nan_to_num(mfe), torch.nan_to_num(mfe32))
     host = imp.run_classifier(clips[:40])
     assert np.array_equal(host, p16[:40].cpu().numpy())
-    if name in ("l476", "l432", "gsc12", "dw3"):
+    if name in ("l476", "l432", "gsc12", "dw3", "zip6"):
         st = m.Streams(imp, 7)
         audio = clips[:14].reshape(7, -1)
         for s in range(8):
@@ -52,6 +52,12 @@ for name in (("l476", "zip6") if quick else ("l476", "l432", "gsc12", "dw3", "zi
         st.close()
     imp.close()
 imp = m.Impulse("l476")
+# tests-only CMVN stage kernel (both paths) and the multi-device host entry
+cep = np.random.default_rng(3).standard_normal((97, 49, 13)).astype(np.float32) * 5
+assert np.array_equal(imp.debug_cmvn_quantise(cep, True), imp.debug_cmvn_quantise(cep, False))
+multi = m.MultiImpulse("l476")
+assert np.array_equal(multi.run_classifier(clips[:101]), imp.run_classifier(clips[:101]))
+multi.close()
 i2s = torch.randint(-2 ** 31, 2 ** 31 - 1, (4 * 16000 * 3,), dtype=torch.int32, device="cuda:0")
 imp.decimate_i2s_device(i2s, 16000 * 3)
 torch.cuda.synchronize()
