@@ -123,8 +123,9 @@ def speechlike_clip(params) -> np.ndarray:
         voiced += (w * _isin(phase * h)) >> 7
     env = (_isin((t * 32768) // ln) * level) >> 15  # half-sine syllable envelope, 0 outside
     env = np.where((n >= on) & (n < on + ln), env, 0)
-    x = (voiced * env) >> 15
-    r = _splitmix64((np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + n.astype(np.uint64)) & _M64)
+    x = (voiced * env) >> 18
+    with np.errstate(over="ignore"):
+        r = _splitmix64((np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + n.astype(np.uint64)) & _M64)
     noise = ((r & np.uint64(0xFFFF)).astype(np.int64) + ((r >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64)) - 65535
     b0, b1 = max(0, on - burst_ms * 16), on
     x = x + np.where((n >= b0) & (n < b1), (noise * burst_level) >> 12, 0) + ((noise * 3) >> 10)

@@ -4,8 +4,9 @@
 uses the committed files.  The reference ships no golden vectors of its own, so these are the
 pinned known answers for every layer of the test pyramid.
 
-Inputs are not stored: they are regenerated from (seed, index) by ei-keyword-spotting_b200/synth.py, except the
-hand-built special clips whose names are recorded.  Stored per model:
+Inputs are not stored: they are regenerated from (seed, index) by ei-keyword-spotting_b200/synth.py; of the hand-built special
+clips the names are recorded, of the speech-like clips (synth.speechlike_clip: integer-only harmonic stacks with formants, a
+syllable envelope and a noise burst, picked per model so that every label it can produce wins) the parameter rows.  Stored per model:
   features   [n,637] float32  extract_mfcc_features output (bit pattern matters)
   probs      [n,L]   float32  run_classifier output
   mel0/energy0/mfcc0          stage taps of clip 0 (mfe output, frame energies, pre-CMVN cepstra)
@@ -30,6 +31,7 @@ from oracle_lib import RefOracle  # noqa: E402
 
 N_SYNTH = 40
 GOLDEN_SEED = 0xE1D5
+N_SPEECH_CANDIDATES = 1500  # speech-like clips searched per model so that every label it can produce wins in the goldens
 # arena tensors (index: byte range) that no later node overwrites, i.e. that can still be read after invoke;
 # plus the two output-sized tensors at the end of every graph
 INTACT = {19: (210, 1470), 21: (0, 210), 23: (0, 70), 25: (10, 70), 27: (0, 10)}     # L476 topology (l476, l432, gsc12, l476f32)
@@ -49,11 +51,41 @@ def crafted_features(n_labels_seed: int) -> np.ndarray:
     return F
 
 
+def speech_candidates():
+    """parameter rows of synth.speechlike_clip: (f0, glide, vowel a, vowel b, onset ms, length ms, level, burst ms, burst level, seed)"""
+    rng = np.random.default_rng(42)
+    n = N_SPEECH_CANDIDATES
+    return np.stack([rng.integers(85, 260, n), rng.integers(-60, 80, n), rng.integers(0, 8, n), rng.integers(0, 8, n), rng.integers(50, 500, n),
+                     rng.integers(150, 700, n), rng.integers(2000, 30000, n), rng.integers(0, 120, n), rng.integers(0, 6000, n),
+                     rng.integers(0, 1 << 30, n)], 1).astype(np.int64)
+
+
+def pick_speech_clips(ref, params, cand_clips):
+    """for every label that wins on some candidate: the three candidates where it wins with the highest and the one where it wins
+    with the lowest probability (a near-tie); for a model on which a single label always wins, six spread-out candidates"""
+    probs = ref.run_classifier_i16(cand_clips)
+    win = probs.argmax(1)
+    chosen = []
+    for lab in range(ref.n_labels):
+        idx = np.nonzero(win == lab)[0]
+        if idx.size == 0:
+            continue
+        order = idx[np.argsort(-probs[idx, lab])]
+        chosen += list(order[:3]) + [order[-1]]
+    if len(set(win)) <= 1:
+        chosen += list(np.argsort(probs.max(1))[:: max(1, len(probs) // 6)][:6])
+    chosen = sorted(set(int(c) for c in chosen))
+    return params[chosen]
+
+
 def main():
+    cand_params = speech_candidates()
+    cand_clips = synth.speechlike_clips(cand_params)
     for mi, name in enumerate(("l476", "l432", "gsc12", "l476f32", "zip6", "dw3")):
         ref = RefOracle(name)
         specials = synth.special_clips()
-        clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values()))])
+        speech_params = pick_speech_clips(ref, cand_params, cand_clips)
+        clips = np.concatenate([synth.synth_clips(N_SYNTH, 0, GOLDEN_SEED), np.stack(list(specials.values())), synth.speechlike_clips(speech_params)])
         feats = ref.mfcc_i16(clips)
         probs = ref.run_classifier_i16(clips)
         mel0, en0 = ref.mfe_i16(clips[0])
@@ -63,7 +95,7 @@ def main():
         feats_f32 = ref.mfcc_f32(xf)
         F = crafted_features(mi)
         nn_probs, tens = ref.run_inference(F, want_tensors=True)
-        out = dict(n_synth=N_SYNTH, seed=GOLDEN_SEED, special_names=np.array(list(specials.keys())),
+        out = dict(n_synth=N_SYNTH, seed=GOLDEN_SEED, special_names=np.array(list(specials.keys())), speech_params=speech_params,
                    features=feats, probs=probs, mel0=mel0, energy0=en0, mfcc0=mfcc0, filterbank=ref.filterbank(),
                    features_f32in=feats_f32, nn_features=F, nn_probs=nn_probs, labels=np.array(ref.labels))
         n_t = len(tens[0])
@@ -77,7 +109,8 @@ def main():
         out["nn_t_out"] = np.stack([t[n_t - 1] for t in tens])
         path = os.path.join(HERE, f"golden_{name}.npz")
         np.savez_compressed(path, **out)
-        print(path, os.path.getsize(path), "bytes;", "argmax histogram", np.bincount(probs.argmax(1), minlength=ref.n_labels))
+        print(path, os.path.getsize(path), "bytes;", len(clips), "clips,", len(np.unique(probs, axis=0)), "distinct probability rows; argmax histogram",
+              np.bincount(probs.argmax(1), minlength=ref.n_labels))
 
 
 if __name__ == "__main__":

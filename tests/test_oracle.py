@@ -18,7 +18,8 @@ def golden(name):
 
 def golden_clips(synth, g):
     sp = synth.special_clips()
-    return np.concatenate([synth.synth_clips(int(g["n_synth"]), 0, int(g["seed"])), np.stack([sp[str(k)] for k in g["special_names"]])])
+    return np.concatenate([synth.synth_clips(int(g["n_synth"]), 0, int(g["seed"])), np.stack([sp[str(k)] for k in g["special_names"]]),
+                           synth.speechlike_clips(g["speech_params"])])
 
 
 def same_floats(a, b):
