@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
     L.eikws_streams_push_i16_device.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32), vp]
     L.eikws_debug_host_plan.argtypes = [C.c_char_p, sz, vp, vp, vp, i32, C.POINTER(i32)]
     L.eikws_debug_cmvn_quantise_host.argtypes = [vp, vp, sz, i32, vp]
+    L.eikws_mix_audio_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz, C.c_float, C.c_float, sz, vp, vp]
     L.eikws_multi_create.argtypes = [C.c_char_p, sz, C.POINTER(i32), i32, C.POINTER(vp)]
     L.eikws_multi_destroy.argtypes = [vp]
     L.eikws_multi_device_count.argtypes = [vp]
@@ -293,6 +294,24 @@ class Impulse:
         out = torch.empty(n_out, dtype=torch.int16, device=i2s.device)
         stream = C.c_void_p(torch.cuda.current_stream(i2s.device).cuda_stream)
         _check(self._lib.eikws_decimate_i2s_device(self._h, C.c_void_p(i2s.data_ptr()), n_out, skip, shift, C.c_void_p(out.data_ptr()), stream))
+        return out
+
+    def mix_audio_device(self, words, word_len, bg, bg_start, word_vol=1.0, bg_vol=0.1):
+        """mix_audio of the dataset tooling (dataset-curation.py:93-137) + PCM_16 conversion for 16 kHz float32 tensors on the device:
+        words [n, stride] float32 (or None: background-only clips) with word_len [n] uint32 valid samples, bg [bg_len] float32,
+        bg_start [n] uint32 -> [n, 16000] int16"""
+        import torch
+        n = int(bg_start.numel())
+        assert bg.is_cuda and bg.dtype == torch.float32 and bg_start.dtype in (torch.int32, torch.uint32) and bg.is_contiguous()
+        assert words is None or (words.dtype == torch.float32 and words.stride(1) == 1 and word_len.dtype in (torch.int32, torch.uint32))
+        out = torch.empty((n, self.raw_sample_count), dtype=torch.int16, device=bg.device)
+        stream = C.c_void_p(torch.cuda.current_stream(bg.device).cuda_stream)
+        max_start = int(bg_start.max().item()) if n else 0
+        _check(self._lib.eikws_mix_audio_device(self._h, C.c_void_p(words.data_ptr()) if words is not None else None,
+                                                C.c_void_p(word_len.data_ptr()) if words is not None else None,
+                                                int(words.stride(0)) if words is not None else 0, C.c_void_p(bg.data_ptr()), int(bg.numel()),
+                                                C.c_void_p(bg_start.data_ptr()), max_start, C.c_float(word_vol), C.c_float(bg_vol), n,
+                                                C.c_void_p(out.data_ptr()), stream))
         return out
 
     def synth_clips_device(self, n_clips, first_clip=0, seed=0xE1D5):

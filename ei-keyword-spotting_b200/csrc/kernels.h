@@ -69,6 +69,9 @@ cudaError_t launch_continuous(const ContinuousArgs &a);
 cudaError_t launch_decimate_i2s(const int32_t *i2s, size_t n_out, int skip, int shift, int16_t *pcm, cudaStream_t st);
 // tests only: CMVN + input quantisation of caller-supplied pre-CMVN cepstra [n][49][13] -> int8 [n][637]; shortcut = certified path
 cudaError_t launch_debug_cmvn_quantise(const DevPlan *plan, const float *cepstra, size_t n, int shortcut, int8_t *q_out, cudaStream_t st);
+// mix_audio arithmetic (dataset-curation.py:93-137) + PCM_16 conversion; words may be null (background-only clips)
+cudaError_t launch_mix_audio(const float *words, const uint32_t *word_len, size_t word_stride, const float *bg, const uint32_t *bg_start,
+                             double half_word_vol, float half_bg_vol, size_t n_clips, int16_t *out, cudaStream_t st);
 cudaError_t launch_synth(int16_t *pcm, size_t n_clips, uint64_t first_clip, uint64_t seed, cudaStream_t st);
 int kernel_threads();
 int debug_tap_floats();  // P[129][49] + logmel[49][33] + cepstra[49][13]

@@ -198,6 +198,16 @@ int eikws_streams_push_f32_host(eikws_streams *s, const float *slices, float bey
  * d_pcm must be 16-byte aligned; d_i2s holds at least skip * n_out words. */
 int eikws_decimate_i2s_device(eikws_handle *h, const int32_t *d_i2s, size_t n_out, int skip, int shift, int16_t *d_pcm, void *stream);
 
+/* The arithmetic of the dataset tooling's mix_audio (dataset-curation.py:93-137) and of its PCM_16 write (:190-206) for material that
+ * is already 16 kHz float32 (the resampling librosa.load does there is NOT part of this call):
+ *   d_pcm[c][i] = PCM16(0.5 * word_vol * word[c][i] + 0.5 * bg_vol * bg[bg_start[c] + i]),  i < raw_sample_count,
+ * word c = d_words + c * word_stride with d_word_len[c] valid samples (shorter: zero-padded, longer: truncated; d_words == NULL:
+ * the script's background-only clips), bg_start[c] <= max_bg_start <= bg_len - raw_sample_count.  PCM16(x) = lrint(x * 32767),
+ * low 16 bits (libsndfile's unclipped double -> short conversion).  One streaming kernel: 8 bytes read, 2 written per sample. */
+int eikws_mix_audio_device(eikws_handle *h, const float *d_words, const uint32_t *d_word_len, size_t word_stride, const float *d_bg,
+                           size_t bg_len, const uint32_t *d_bg_start, size_t max_bg_start, float word_vol, float bg_vol, size_t n_clips,
+                           int16_t *d_pcm, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *eikws_last_error(void); /* thread-local text of the last failure */
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches claim) */

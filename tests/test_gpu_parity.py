@@ -499,3 +499,54 @@ def test_single_clip_calls_from_many_threads_do_not_mix_clips(eikws, impulses, s
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_mix_audio_matches_the_numpy_restatement(impulses):
+    """the dataset tooling's mix_audio + PCM_16 write (dataset-curation.py:93-137, 190-206) as one streaming kernel, against
+    oracle/mix_audio_oracle.py (PARITY UNPINNED: librosa / soundfile are absent, see that module): words shorter and longer than a
+    second, odd lengths, background-only clips, volumes that overflow 16 bits (libsndfile wraps), exact .5 ties of the rounding"""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("mix_audio_oracle", os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "mix_audio_oracle.py"))
+    mo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mo)
+    imp = impulses["l476"]
+    rng = np.random.default_rng(77)
+    n, stride = 257, 20000
+    words = (rng.standard_normal((n, stride)) * 0.3).astype(np.float32)
+    lens = rng.integers(0, stride + 1, n).astype(np.uint32)
+    lens[:6] = [0, 1, 15999, 16000, 16001, 20000]
+    words[6, :16000] = (np.arange(16000) - 8000).astype(np.float32) / np.float32(32767.0)  # x * 32767 lands on integers and .5 ties
+    lens[6] = 16000
+    bg = (rng.standard_normal(16000 * 40) * 0.2).astype(np.float32)
+    bg[:16000] = 0.0
+    starts = rng.integers(0, len(bg) - 16000 + 1, n).astype(np.uint32)
+    starts[6] = 0
+    starts[7] = len(bg) - 16000
+    d_words, d_lens = torch.from_numpy(words).cuda(), torch.from_numpy(lens.view(np.int32)).cuda()
+    d_bg, d_starts = torch.from_numpy(bg).cuda(), torch.from_numpy(starts.view(np.int32)).cuda()
+    for wv, bv in ((1.0, 0.1), (0.7, 1.0), (9.0, 3.0), (2.0, 0.0)):
+        got = imp.mix_audio_device(d_words, d_lens, d_bg, d_starts, wv, bv).cpu().numpy()
+        for c in range(n):
+            want = mo.to_pcm16(mo.mix_audio(words[c, :lens[c]], bg, int(starts[c]), wv, bv))
+            assert np.array_equal(got[c], want), f"clip {c} word_vol {wv} bg_vol {bv}"
+    got = imp.mix_audio_device(None, None, d_bg, d_starts, 1.0, 0.25).cpu().numpy()  # the script's _noise clips
+    for c in (0, 7, 100):
+        assert np.array_equal(got[c], mo.to_pcm16(mo.mix_audio(None, bg, int(starts[c]), 1.0, 0.25)))
+    # the mixed clips feed the classifier like any other int16 batch
+    assert imp.run_classifier_device(imp.mix_audio_device(d_words, d_lens, d_bg, d_starts, 1.0, 0.1)).shape == (n, imp.label_count)
+    # throughput of the streaming kernel (8 B read + 2 B written per sample), for DESIGN.md
+    big = 8192
+    w2 = torch.randn((big, 16000), device="cuda") * 0.3
+    l2 = torch.full((big,), 16000, dtype=torch.int32, device="cuda")
+    s2 = torch.randint(0, len(bg) - 16000, (big,), dtype=torch.int32, device="cuda")
+    imp.mix_audio_device(w2, l2, d_bg, s2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        imp.mix_audio_device(w2, l2, d_bg, s2)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = 10 * big * 16000 * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    print(f"mix_audio: {gbs:.0f} GB/s algorithmic ({10 * big / (e0.elapsed_time(e1) * 1e-3) / 1e6:.1f} M clips/s)")
+    assert gbs > 500

@@ -254,3 +254,23 @@ def test_multi_device_api_without_gpu_fails_loudly(eikws):
     lib = eikws.load_library()
     assert lib.eikws_multi_device_count(None) == 0 and lib.eikws_multi_handle(None, 0) is None
     assert lib.eikws_host_alloc(64) is None and b"cudaHostAlloc" in lib.eikws_last_error()
+
+
+def test_mix_audio_restatement_known_answers():
+    """oracle/mix_audio_oracle.py (numpy restatement of dataset-curation.py:93-137 + the PCM_16 write; PARITY UNPINNED, see the
+    module) on values worked out by hand: padding, truncation, the float32 background product, round-half-even, 16-bit wrap"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mix_audio_oracle", os.path.join(ROOT, "oracle", "mix_audio_oracle.py"))
+    mo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mo)
+    bg = np.zeros(40000, np.float32)
+    bg[100:16100] = np.float32(0.5)
+    x = mo.mix_audio(np.array([1.0, -1.0, 0.25], np.float32), bg, 100, word_vol=1.0, bg_vol=0.1)
+    assert x.dtype == np.float64 and x.shape == (16000,)
+    b = float(np.float32(0.05) * np.float32(0.5))  # the background term is a float32 product
+    assert x[0] == 0.5 + b and x[1] == -0.5 + b and x[2] == 0.125 + b and x[3] == b and x[15999] == b  # zero padding behind the word
+    long_word = np.arange(20000, dtype=np.float32) / np.float32(20000)
+    assert np.array_equal(mo.mix_audio(long_word, np.zeros(16000, np.float32), 0, 2.0, 1.0), long_word[:16000].astype(np.float64))  # truncation
+    assert np.array_equal(mo.mix_audio(None, bg, 100, 3.0, 2.0), np.full(16000, 0.5))  # background-only clip
+    pcm = mo.to_pcm16(np.array([0.0, 1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767, 2.0, -1.0001]))
+    assert pcm.tolist() == [0, 32767, -32767, 0, 2, 2, -2, 32766]  # ties to even; 65534 and -32770 wrap through 16 bits
