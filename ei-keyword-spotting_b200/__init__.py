@@ -56,6 +56,7 @@ def load_library() -> C.CDLL:
     L.eikws_set_tensor_core.argtypes = [vp, i32]
     L.eikws_set_cmvn_shortcut.argtypes = [vp, i32]
     L.eikws_set_work_claiming.argtypes = [vp, i32]
+    L.eikws_set_pipelined.argtypes = [vp, i32]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -162,6 +163,10 @@ class Impulse:
     def set_work_claiming(self, on: bool):
         """work-claiming schedule of the shortcut kernel (frame pairs and the UMMA issue claimed from shared counters)"""
         _check(self._lib.eikws_set_work_claiming(self._h, 1 if on else 0))
+
+    def set_pipelined(self, on: bool):
+        """the software-pipelined classify kernel: FFT of clip s interleaved, warp by warp, with the post-FFT slices of clip s-1"""
+        _check(self._lib.eikws_set_pipelined(self._h, 1 if on else 0))
 
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))

@@ -32,6 +32,7 @@ struct eikws_handle {
     int ctas_per_sm = 4;    // clip groups (160 threads each) resident per SM
     int clips_per_cta = 2;  // clip groups per CTA: 2 CTAs x 2 groups measured best (profiles/r1_ab_clip_groups.txt)
     int skew_ns = 14000;  // start offset between the CTAs that share an SM (see kernels.cu)
+    int pipelined = 0;      // software-pipelined classify kernel (kernels.cu eikws_pipelined_kernel)
     int work_claiming = 1;  // work-claiming schedule of the shortcut kernel (kDyn in kernels.cu)
     int cmvn_shortcut = 1;  // certified CMVN shortcut of the tensor-core variant (kernels.cu cmvn_certified; exact fallback inside the kernel)
     int tensor_core = 1;  // block 1 of the fused classifier as a tcgen05 UMMA (when the plan allows it; +2.4 %, profiles/r1_ab_tensor_core_block1.txt)
@@ -110,6 +111,7 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.nn_tc = h->tensor_core != 0 && h->host.dev.nn.fused.tc_enabled != 0 && dbg == nullptr;
     a.cmvn_certified = h->cmvn_shortcut != 0;
     a.work_claiming = h->work_claiming != 0;
+    a.pipelined = h->pipelined != 0;
     if (a.nn_float && qfeat) return fail(EIKWS_ERR_BAD_ARG, "a float32 model has no quantised input tensor");
     a.probs = probs;
     a.features_out = feat;
@@ -255,6 +257,11 @@ int eikws_set_cmvn_shortcut(eikws_handle *h, int on) {  // tuning knob (not in t
 int eikws_set_work_claiming(eikws_handle *h, int on) {  // tuning knob (not in the public header)
     if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
     h->work_claiming = on;
+    return EIKWS_OK;
+}
+int eikws_set_pipelined(eikws_handle *h, int on) {  // tuning knob: the software-pipelined classify kernel
+    if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
+    h->pipelined = on;
     return EIKWS_OK;
 }
 int eikws_set_skew_ns(eikws_handle *h, int ns) {  // tuning knob (not in the public header)

@@ -20,6 +20,7 @@ struct LaunchArgs {
     bool nn_float = false;               // float32 graph (NnDev.float_mode)
     bool nn_tc = false;                  // block 1 of the fused classifier on the tensor core (NnFusedDev.tc_enabled, 2 clip groups per CTA)
     bool cmvn_certified = false;         // certified CMVN shortcut (tensor-core variant, no float feature output): see cmvn_certified()
+    bool pipelined = false;              // with cmvn_certified + nn_tc: the software-pipelined kernel (eikws_pipelined_kernel: FFT of clip s interleaved with the post-FFT slices of clip s-1)
     bool work_claiming = false;          // with cmvn_certified: frame pairs and the UMMA issue are claimed dynamically (kDyn in kernels.cu)
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]

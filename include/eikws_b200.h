@@ -223,6 +223,7 @@ int eikws_set_clips_per_cta(eikws_handle *h, int n); /* clip groups per CTA: 1, 
 int eikws_set_tensor_core(eikws_handle *h, int on);  /* block 1 of the fused classifier as a tcgen05 UMMA                */
 int eikws_set_cmvn_shortcut(eikws_handle *h, int on);/* certified CMVN shortcut (0: every chain with the exact sequence) */
 int eikws_set_work_claiming(eikws_handle *h, int on);/* work-claiming schedule of the shortcut kernel                    */
+int eikws_set_pipelined(eikws_handle *h, int on);     /* software-pipelined classify kernel (two clips in different stages per CTA) */
 int eikws_set_skew_ns(eikws_handle *h, int ns);      /* start offset between the CTAs that share an SM                   */
 
 /* ---- parity taps (tests only) --------------------------------------------------------------- */

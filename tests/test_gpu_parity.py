@@ -550,3 +550,40 @@ def test_mix_audio_matches_the_numpy_restatement(impulses):
     gbs = 10 * big * 16000 * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
     print(f"mix_audio: {gbs:.0f} GB/s algorithmic ({10 * big / (e0.elapsed_time(e1) * 1e-3) / 1e6:.1f} M clips/s)")
     assert gbs > 500
+
+
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3"])
+def test_pipelined_kernel_is_bit_identical(name, impulses, synth):
+    """eikws_pipelined_kernel (every warp interleaves the FFT of clip s with the post-FFT slices of clip s-1; mbarrier-linked slices,
+    one CTA barrier per clip) against the goldens of the unmodified reference, the oracle's int8 input tensor, the phase-by-phase
+    kernel on 65,536 fresh clips, and ragged batch sizes from one clip up (short CTAs: 1, 2, 3 clips per CTA and uneven tails)"""
+    import torch
+    imp = impulses[name]
+    g = golden(name)
+    clips = golden_clips(synth, g)
+    port = PortOracle(name)
+    _, tens = port.run_inference(g["features"], want_tensors=True)
+    want_q = np.stack([t[0] for t in tens]).view(np.int8)
+    n = 65536
+    d = imp.synth_clips_device(n, first_clip=424242, seed=0xBEEF)
+    p_ref, q_ref = imp.run_classifier_taps_device(d)
+    try:
+        imp.set_pipelined(True)
+        before = imp.launch_count
+        probs, q = imp.run_classifier_taps_device(torch.from_numpy(clips).to("cuda:0"))
+        torch.cuda.synchronize()
+        assert np.array_equal(q.cpu().numpy(), want_q)
+        assert np.array_equal(probs.cpu().numpy(), g["probs"])
+        assert np.array_equal(imp.run_classifier(clips), g["probs"])
+        p1, q1 = imp.run_classifier_taps_device(d)
+        p1b = imp.run_classifier_device(d)
+        torch.cuda.synchronize()
+        bad = (q1 != q_ref).any(dim=1).nonzero().flatten()
+        assert bad.numel() == 0, f"clips whose quantised features differ: {bad[:10].tolist()}"
+        assert torch.equal(p1, p_ref) and torch.equal(p1b, p_ref)
+        for m in (1, 2, 3, 5, 295, 296, 297, 591, 593, 887, 889, 1185, 4099):
+            assert torch.equal(imp.run_classifier_device(d[:m].contiguous()), p_ref[:m]), f"n={m}"
+            assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p_ref[n - m:]), f"tail n={m}"
+        assert imp.launch_count > before
+    finally:
+        imp.set_pipelined(False)

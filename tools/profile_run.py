@@ -14,6 +14,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 imp = m.Impulse("l476")
 if os.environ.get("EIKWS_TC", "") != "":  # 0 = dp4a block 1, 1 = UMMA, 2 = UMMA + run-ahead schedule
     imp.set_tensor_core(int(os.environ["EIKWS_TC"]))
+if os.environ.get("EIKWS_PIPE", "") != "":  # 1 = the software-pipelined kernel
+    imp.set_pipelined(os.environ["EIKWS_PIPE"] == "1")
 clips = imp.synth_clips_device(n)
 out = torch.empty((n, imp.label_count), dtype=torch.float32, device="cuda:0")
 for _ in range(reps):
