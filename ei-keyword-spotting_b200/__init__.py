@@ -84,7 +84,7 @@ def load_library() -> C.CDLL:
     L.eikws_streams_push_i16_device.argtypes = [vp, vp, C.c_float, vp, C.POINTER(i32), vp]
     L.eikws_debug_host_plan.argtypes = [C.c_char_p, sz, vp, vp, vp, i32, C.POINTER(i32)]
     L.eikws_debug_cmvn_quantise_host.argtypes = [vp, vp, sz, i32, vp]
-    L.eikws_mix_audio_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz, C.c_float, C.c_float, sz, vp, vp]
+    L.eikws_mix_audio_device.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz, C.c_double, C.c_double, sz, vp, vp]
     L.eikws_multi_create.argtypes = [C.c_char_p, sz, C.POINTER(i32), i32, C.POINTER(vp)]
     L.eikws_multi_destroy.argtypes = [vp]
     L.eikws_multi_device_count.argtypes = [vp]
@@ -315,7 +315,7 @@ class Impulse:
         _check(self._lib.eikws_mix_audio_device(self._h, C.c_void_p(words.data_ptr()) if words is not None else None,
                                                 C.c_void_p(word_len.data_ptr()) if words is not None else None,
                                                 int(words.stride(0)) if words is not None else 0, C.c_void_p(bg.data_ptr()), int(bg.numel()),
-                                                C.c_void_p(bg_start.data_ptr()), max_start, C.c_float(word_vol), C.c_float(bg_vol), n,
+                                                C.c_void_p(bg_start.data_ptr()), max_start, C.c_double(word_vol), C.c_double(bg_vol), n,
                                                 C.c_void_p(out.data_ptr()), stream))
         return out
 

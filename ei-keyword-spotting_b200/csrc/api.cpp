@@ -319,7 +319,7 @@ int eikws_decimate_i2s_device(eikws_handle *h, const int32_t *d_i2s, size_t n_ou
 // d_pcm[c][i] = PCM16(0.5 * word_vol * word[c][i] + 0.5 * bg_vol * bg[bg_start[c] + i]).  d_words may be NULL (the script's
 // background-only clips, word_path=None); word c holds word_len[c] valid samples (zero-padded / truncated to one second).
 int eikws_mix_audio_device(eikws_handle *h, const float *d_words, const uint32_t *d_word_len, size_t word_stride, const float *d_bg, size_t bg_len,
-                           const uint32_t *d_bg_start, size_t max_bg_start, float word_vol, float bg_vol, size_t n_clips, int16_t *d_pcm,
+                           const uint32_t *d_bg_start, size_t max_bg_start, double word_vol, double bg_vol, size_t n_clips, int16_t *d_pcm,
                            void *stream) {
     if (!h || !d_bg || !d_bg_start || !d_pcm || (d_words && !d_word_len)) return fail(EIKWS_ERR_BAD_ARG, "null argument");
     if (bg_len < static_cast<size_t>(kSamples) || max_bg_start > bg_len - kSamples)
@@ -329,8 +329,8 @@ int eikws_mix_audio_device(eikws_handle *h, const float *d_words, const uint32_t
     if (n_clips == 0) return EIKWS_OK;
     DeviceGuard guard(h->device);
     // 0.5 * word_vol is a Python float product (double); 0.5 * bg_vol multiplies a float32 array, i.e. is rounded to float32 first
-    const double half_word = 0.5 * static_cast<double>(word_vol);
-    const float half_bg = static_cast<float>(0.5 * static_cast<double>(bg_vol));
+    const double half_word = 0.5 * word_vol;
+    const float half_bg = static_cast<float>(0.5 * bg_vol);
     cudaError_t e = launch_mix_audio(d_words, d_word_len, word_stride, d_bg, d_bg_start, half_word, half_bg, n_clips, d_pcm, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "mix_audio launch");
     h->launches++;

@@ -203,9 +203,9 @@ int eikws_decimate_i2s_device(eikws_handle *h, const int32_t *d_i2s, size_t n_ou
  *   d_pcm[c][i] = PCM16(0.5 * word_vol * word[c][i] + 0.5 * bg_vol * bg[bg_start[c] + i]),  i < raw_sample_count,
  * word c = d_words + c * word_stride with d_word_len[c] valid samples (shorter: zero-padded, longer: truncated; d_words == NULL:
  * the script's background-only clips), bg_start[c] <= max_bg_start <= bg_len - raw_sample_count.  PCM16(x) = lrint(x * 32767),
- * low 16 bits (libsndfile's unclipped double -> short conversion).  One streaming kernel: 8 bytes read, 2 written per sample. */
+ * low 16 bits (libsndfile's unclipped double -> short conversion).  The volumes are doubles because the script's are Python floats.  One streaming kernel: 8 bytes read, 2 written per sample. */
 int eikws_mix_audio_device(eikws_handle *h, const float *d_words, const uint32_t *d_word_len, size_t word_stride, const float *d_bg,
-                           size_t bg_len, const uint32_t *d_bg_start, size_t max_bg_start, float word_vol, float bg_vol, size_t n_clips,
+                           size_t bg_len, const uint32_t *d_bg_start, size_t max_bg_start, double word_vol, double bg_vol, size_t n_clips,
                            int16_t *d_pcm, void *stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
