@@ -57,6 +57,9 @@ def load_library() -> C.CDLL:
     L.eikws_set_cmvn_shortcut.argtypes = [vp, i32]
     L.eikws_set_work_claiming.argtypes = [vp, i32]
     L.eikws_set_pipelined.argtypes = [vp, i32]
+    L.eikws_set_split.argtypes = [vp, i32]
+    L.eikws_set_kernel_timing.argtypes = [vp, i32]
+    L.eikws_split_kernel_ms.argtypes = [vp, vp]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -167,6 +170,20 @@ class Impulse:
     def set_pipelined(self, on: bool):
         """the software-pipelined classify kernel: FFT of clip s interleaved, warp by warp, with the post-FFT slices of clip s-1"""
         _check(self._lib.eikws_set_pipelined(self._h, 1 if on else 0))
+
+    def set_split(self, on: bool):
+        """the two-kernel classify path (int16 clips): barrier-free spectral kernel, then the cepstral / classifier kernel"""
+        _check(self._lib.eikws_set_split(self._h, 1 if on else 0))
+
+    def set_kernel_timing(self, on: bool):
+        """record CUDA events around the two kernels of every split launch (see split_kernel_ms)"""
+        _check(self._lib.eikws_set_kernel_timing(self._h, 1 if on else 0))
+
+    def split_kernel_ms(self):
+        """(spectral kernel ms, cepstral / classifier kernel ms) of the last split launch; waits for it"""
+        ms = (C.c_float * 2)()
+        _check(self._lib.eikws_split_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1])
 
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))

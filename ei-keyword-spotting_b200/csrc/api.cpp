@@ -33,6 +33,11 @@ struct eikws_handle {
     int clips_per_cta = 2;  // clip groups per CTA: 2 CTAs x 2 groups measured best (profiles/r1_ab_clip_groups.txt)
     int skew_ns = 14000;  // start offset between the CTAs that share an SM (see kernels.cu)
     int pipelined = 0;      // software-pipelined classify kernel (kernels.cu eikws_pipelined_kernel)
+    int split = 1;          // two-kernel classify path for int16 clips (kernels.cu eikws_logmel_kernel -> eikws_cepstral_kernel)
+    size_t split_chunk_clips = 65536;  // clips per kernel pair: bounds the hand-over scratch (6,480 B per clip) at 425 MB
+    cudaEvent_t split_ev[3] = {nullptr, nullptr, nullptr};  // eikws_set_kernel_timing: events around the two kernels of the last split launch
+    int kernel_timing = 0;
+    cudaMemPool_t pool = nullptr;      // stream-ordered allocations of that scratch: no state shared between callers' streams
     int work_claiming = 1;  // work-claiming schedule of the shortcut kernel (kDyn in kernels.cu)
     int cmvn_shortcut = 1;  // certified CMVN shortcut of the tensor-core variant (kernels.cu cmvn_certified; exact fallback inside the kernel)
     int tensor_core = 1;  // block 1 of the fused classifier as a tcgen05 UMMA (when the plan allows it; +2.4 %, profiles/r1_ab_tensor_core_block1.txt)
@@ -124,7 +129,31 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.pre_cof = h->host.dev.mfcc.pre_cof;
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
     a.stream = st;
-    cudaError_t e = launch_run_classifier(a);
+    cudaError_t e;
+    if (h->split && !h->pipelined && clips && !f32 && !features_in && run_nn && a.nn_fused && !a.nn_float && a.nn_tc && a.cmvn_certified && !feat && !dbg &&
+        h->clips_per_cta == 2) {
+        // two kernels per chunk, the log-mel records in between in stream-ordered scratch
+        const size_t L = h->graph.labels.size();
+        for (size_t off = 0; off < n; off += h->split_chunk_clips) {
+            const size_t m = n - off < h->split_chunk_clips ? n - off : h->split_chunk_clips;
+            void *scratch = nullptr;
+            if ((e = cudaMallocFromPoolAsync(&scratch, split_scratch_bytes(m), h->pool, st)) != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(log-mel scratch)");
+            a.clips = static_cast<const int16_t *>(clips) + off * static_cast<size_t>(kSamples);
+            a.n_clips = m;
+            a.probs = probs + off * L;
+            a.qfeatures_out = qfeat ? qfeat + off * static_cast<size_t>(kFeatures) : nullptr;
+            a.split = true;
+            a.logmel = static_cast<float *>(scratch);
+            a.split_events = h->kernel_timing ? h->split_ev : nullptr;
+            e = launch_run_classifier(a);
+            cudaError_t e2 = cudaFreeAsync(scratch, st);
+            if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+            if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync(log-mel scratch)");
+            h->launches += 2;
+        }
+        return EIKWS_OK;
+    }
+    e = launch_run_classifier(a);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     h->launches++;
     return EIKWS_OK;
@@ -206,6 +235,17 @@ int eikws_create(const void *model_blob, size_t bytes, int device, eikws_handle 
         delete h;
         return cuda_fail(e, "cudaStreamCreate");
     }
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        uint64_t keep = UINT64_MAX;  // freed scratch stays in the pool: the next launch's allocation costs microseconds
+        if ((e = cudaMemPoolCreate(&h->pool, &props)) != cudaSuccess || (e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) {
+            eikws_destroy(h);
+            return cuda_fail(e, "cudaMemPoolCreate");
+        }
+    }
     *out = h;
     return EIKWS_OK;
 }
@@ -220,6 +260,12 @@ void eikws_destroy(eikws_handle *h) {
     if (h->d_feat) cudaFree(h->d_feat);
     if (h->d_qfeat) cudaFree(h->d_qfeat);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (cudaEvent_t ev : h->split_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->pool) {
+        cudaDeviceSynchronize();  // stream-ordered frees of the scratch may still be pending on callers' streams
+        cudaMemPoolDestroy(h->pool);
+    }
     free_plan(h->dev);
     delete h;
 }
@@ -262,6 +308,35 @@ int eikws_set_work_claiming(eikws_handle *h, int on) {  // tuning knob (not in t
 int eikws_set_pipelined(eikws_handle *h, int on) {  // tuning knob: the software-pipelined classify kernel
     if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
     h->pipelined = on;
+    return EIKWS_OK;
+}
+int eikws_set_split(eikws_handle *h, int on) {  // tuning knob: the two-kernel classify path (spectral kernel + cepstral / classifier kernel)
+    if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
+    h->split = on;
+    return EIKWS_OK;
+}
+// measurement aid (bench.py's roofline of the dominant kernel): with timing on, every split launch records CUDA events around its two
+// kernels on the launch stream; eikws_split_kernel_ms waits for the last launch and returns {spectral kernel, cepstral kernel} in ms
+int eikws_set_kernel_timing(eikws_handle *h, int on) {
+    if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
+    DeviceGuard guard(h->device);
+    if (on)
+        for (cudaEvent_t &ev : h->split_ev)
+            if (!ev) {
+                cudaError_t e = cudaEventCreate(&ev);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+            }
+    h->kernel_timing = on;
+    return EIKWS_OK;
+}
+int eikws_split_kernel_ms(eikws_handle *h, float *ms2) {
+    if (!h || !ms2) return EIKWS_ERR_BAD_ARG;
+    if (!h->split_ev[2]) return fail(EIKWS_ERR_BAD_ARG, "kernel timing is off");
+    DeviceGuard guard(h->device);
+    cudaError_t e = cudaEventSynchronize(h->split_ev[2]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms2[0], h->split_ev[0], h->split_ev[1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms2[1], h->split_ev[1], h->split_ev[2]);
+    if (e != cudaSuccess) return cuda_fail(e, "split kernel timing (no split launch recorded yet?)");
     return EIKWS_OK;
 }
 int eikws_set_skew_ns(eikws_handle *h, int ns) {  // tuning knob (not in the public header)

@@ -21,6 +21,9 @@ struct LaunchArgs {
     bool nn_tc = false;                  // block 1 of the fused classifier on the tensor core (NnFusedDev.tc_enabled, 2 clip groups per CTA)
     bool cmvn_certified = false;         // certified CMVN shortcut (tensor-core variant, no float feature output): see cmvn_certified()
     bool pipelined = false;              // with cmvn_certified + nn_tc: the software-pipelined kernel (eikws_pipelined_kernel: FFT of clip s interleaved with the post-FFT slices of clip s-1)
+    bool split = false;                  // with cmvn_certified + nn_tc, int16 clips: the two-kernel path (eikws_logmel_kernel -> eikws_cepstral_kernel); needs logmel
+    float *logmel = nullptr;             // device scratch of split_scratch_bytes(n_clips): the log-mel records handed from the first kernel to the second
+    cudaEvent_t *split_events = nullptr; // optional, 3 events: recorded before the first kernel, between the two, after the second
     bool work_claiming = false;          // with cmvn_certified: frame pairs and the UMMA issue are claimed dynamically (kDyn in kernels.cu)
     float *probs = nullptr;              // device: [n_clips][labels]
     float *features_out = nullptr;       // device, optional: [n_clips][637]
@@ -36,6 +39,7 @@ struct LaunchArgs {
 };
 
 cudaError_t launch_run_classifier(const LaunchArgs &a);
+size_t split_scratch_bytes(size_t n_clips);  // LaunchArgs::logmel for a split launch of n_clips (at most 131,072 clips per launch)
 
 // the sibling MFE DSP block: [n_clips][49 * 32] features
 struct MfeArgs {

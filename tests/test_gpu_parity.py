@@ -587,3 +587,42 @@ def test_pipelined_kernel_is_bit_identical(name, impulses, synth):
         assert imp.launch_count > before
     finally:
         imp.set_pipelined(False)
+
+
+@pytest.mark.parametrize("name", ["l476", "l432", "gsc12", "dw3"])
+def test_split_kernels_are_bit_identical(name, impulses, synth):
+    """the two-kernel classify path (eikws_logmel_kernel: a warp per eight frames of the batch's frame sequence, no CTA barrier;
+    eikws_cepstral_kernel: DCT / certified CMVN / int8 CNN of one clip per CTA) against the goldens of the unmodified reference, the
+    oracle's int8 input tensor, the fused phase-by-phase kernel on 65,536 fresh clips, and ragged batch sizes from one clip up (work
+    units that straddle clips, units beyond the batch, CTAs with 0 / 1 / 2 clips, a chunk boundary of the hand-over scratch)"""
+    import torch
+    imp = impulses[name]
+    g = golden(name)
+    clips = golden_clips(synth, g)
+    port = PortOracle(name)
+    _, tens = port.run_inference(g["features"], want_tensors=True)
+    want_q = np.stack([t[0] for t in tens]).view(np.int8)
+    n = 65536 + 4099  # more than one chunk of the scratch
+    d = imp.synth_clips_device(n, first_clip=515151, seed=0xFACE)
+    try:
+        imp.set_split(False)
+        p_ref, q_ref = imp.run_classifier_taps_device(d)
+        imp.set_split(True)
+        before = imp.launch_count
+        probs, q = imp.run_classifier_taps_device(torch.from_numpy(clips).to("cuda:0"))
+        torch.cuda.synchronize()
+        assert imp.launch_count == before + 2, "the split path launches two kernels per chunk"
+        assert np.array_equal(q.cpu().numpy(), want_q)
+        assert np.array_equal(probs.cpu().numpy(), g["probs"])
+        assert np.array_equal(imp.run_classifier(clips), g["probs"])
+        p1, q1 = imp.run_classifier_taps_device(d)
+        p1b = imp.run_classifier_device(d)
+        torch.cuda.synchronize()
+        bad = (q1 != q_ref).any(dim=1).nonzero().flatten()
+        assert bad.numel() == 0, f"clips whose quantised features differ: {bad[:10].tolist()}"
+        assert torch.equal(p1, p_ref) and torch.equal(p1b, p_ref)
+        for m in (1, 2, 3, 5, 7, 8, 9, 163, 739, 740, 741, 1479, 1481, 2961, 4099):
+            assert torch.equal(imp.run_classifier_device(d[:m].contiguous()), p_ref[:m]), f"n={m}"
+            assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p_ref[n - m:]), f"tail n={m}"
+    finally:
+        imp.set_split(True)

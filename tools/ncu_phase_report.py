@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Summarise an ncu report of the fused kernel: headline metrics + instruction / stall-sample share per
-barrier-delimited phase (SASS source page).  usage: ncu_phase_report.py <report.ncu-rep> <n_clips>"""
+barrier-delimited phase (SASS source page).  usage: ncu_phase_report.py <report.ncu-rep> <n_clips> [kernel-name regex]"""
 import csv
 import io
 import subprocess
 import sys
 
 rep, n_clips = sys.argv[1], int(sys.argv[2])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, *sel, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 d = dict(zip(rows[0], rows[2]))
 keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -23,9 +24,15 @@ for k in keys:
 inst = float(d['smsp__inst_executed.sum'])
 print(f"per clip: {inst / n_clips:.0f} warp instructions; dram read {float(d['dram__bytes_read.sum']) * 1e6 / n_clips:.0f} B "
       f"(unit {rows[1][rows[0].index('dram__bytes_read.sum')]})")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+# one section per kernel: a "Kernel Name" row, the header row, the instruction rows; take the first section that matches
+import re
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next((i for i in starts if len(sys.argv) <= 3 or re.search(sys.argv[3], rows[i][1])), starts[0])
+end = next((i for i in starts if i > pick), len(rows))
+hdr = rows[pick + 1]
+data = [r for r in rows[pick + 2:end] if len(r) >= len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 seg, cur = [], None

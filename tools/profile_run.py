@@ -16,6 +16,8 @@ if os.environ.get("EIKWS_TC", "") != "":  # 0 = dp4a block 1, 1 = UMMA, 2 = UMMA
     imp.set_tensor_core(int(os.environ["EIKWS_TC"]))
 if os.environ.get("EIKWS_PIPE", "") != "":  # 1 = the software-pipelined kernel
     imp.set_pipelined(os.environ["EIKWS_PIPE"] == "1")
+if os.environ.get("EIKWS_SPLIT", "") != "":  # 0 = the fused kernel, 1 = the two-kernel path (default)
+    imp.set_split(os.environ["EIKWS_SPLIT"] == "1")
 clips = imp.synth_clips_device(n)
 out = torch.empty((n, imp.label_count), dtype=torch.float32, device="cuda:0")
 for _ in range(reps):
