@@ -59,7 +59,7 @@ def load_library() -> C.CDLL:
     L.eikws_set_pipelined.argtypes = [vp, i32]
     L.eikws_set_split.argtypes = [vp, i32]
     L.eikws_set_kernel_timing.argtypes = [vp, i32]
-    L.eikws_split_kernel_ms.argtypes = [vp, vp]
+    L.eikws_split_kernel_ms.argtypes = [vp, vp, vp]
     L.eikws_classify_i16_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_classify_f32_device.argtypes = [vp, vp, sz, vp, vp]
     L.eikws_features_i16_device.argtypes = [vp, vp, sz, vp, vp, vp]
@@ -180,10 +180,12 @@ class Impulse:
         _check(self._lib.eikws_set_kernel_timing(self._h, 1 if on else 0))
 
     def split_kernel_ms(self):
-        """(spectral kernel ms, cepstral / classifier kernel ms) of the last split launch; waits for it"""
+        """(spectral kernel ms, cepstral / classifier kernel ms, launches): averages per launch over the split launches since timing was
+        switched on or since the last call; waits for them"""
         ms = (C.c_float * 2)()
-        _check(self._lib.eikws_split_kernel_ms(self._h, ms))
-        return float(ms[0]), float(ms[1])
+        cnt = C.c_uint64(0)
+        _check(self._lib.eikws_split_kernel_ms(self._h, ms, C.byref(cnt)))
+        return float(ms[0]), float(ms[1]), int(cnt.value)
 
     def set_skew_ns(self, ns: int):
         _check(self._lib.eikws_set_skew_ns(self._h, ns))

@@ -35,7 +35,13 @@ struct eikws_handle {
     int pipelined = 0;      // software-pipelined classify kernel (kernels.cu eikws_pipelined_kernel)
     int split = 1;          // two-kernel classify path for int16 clips (kernels.cu eikws_logmel_kernel -> eikws_cepstral_kernel)
     size_t split_chunk_clips = 65536;  // clips per kernel pair: bounds the hand-over scratch (6,480 B per clip) at 425 MB
-    cudaEvent_t split_ev[3] = {nullptr, nullptr, nullptr};  // eikws_set_kernel_timing: events around the two kernels of the last split launch
+    // eikws_set_kernel_timing: CUDA events around the two kernels of every split launch (a ring of triples, harvested when it is full
+    // or when eikws_split_kernel_ms asks), accumulated per kernel
+    static constexpr int kEvRing = 32;
+    cudaEvent_t split_ev[kEvRing][3] = {};
+    int ev_used = 0;
+    double ev_ms[2] = {0.0, 0.0};
+    uint64_t ev_launches = 0;
     int kernel_timing = 0;
     cudaMemPool_t pool = nullptr;      // stream-ordered allocations of that scratch: no state shared between callers' streams
     int work_claiming = 1;  // work-claiming schedule of the shortcut kernel (kDyn in kernels.cu)
@@ -100,6 +106,25 @@ int grid_for(const eikws_handle *h, size_t n_clips) {
     return static_cast<int>(g ? g : 1);
 }
 
+// add the recorded event triples to the per-kernel sums (waits for the launches they belong to)
+cudaError_t harvest_split_events(eikws_handle *h) {
+    for (int i = 0; i < h->ev_used; i++) {
+        cudaError_t e = cudaEventSynchronize(h->split_ev[i][2]);
+        float a = 0.0f, b = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&a, h->split_ev[i][0], h->split_ev[i][1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, h->split_ev[i][1], h->split_ev[i][2]);
+        if (e != cudaSuccess) {
+            h->ev_used = 0;
+            return e;
+        }
+        h->ev_ms[0] += a;
+        h->ev_ms[1] += b;
+        h->ev_launches++;
+    }
+    h->ev_used = 0;
+    return cudaSuccess;
+}
+
 int launch(eikws_handle *h, const void *clips, bool f32, const float *features_in, size_t n, bool run_nn, float *probs,
            float *feat, int8_t *qfeat, cudaStream_t st, float *dbg = nullptr) {
     if (n == 0) return EIKWS_OK;
@@ -144,7 +169,11 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
             a.qfeatures_out = qfeat ? qfeat + off * static_cast<size_t>(kFeatures) : nullptr;
             a.split = true;
             a.logmel = static_cast<float *>(scratch);
-            a.split_events = h->kernel_timing ? h->split_ev : nullptr;
+            a.split_events = nullptr;
+            if (h->kernel_timing) {
+                if (h->ev_used == eikws_handle::kEvRing && (e = harvest_split_events(h)) != cudaSuccess) return cuda_fail(e, "split kernel timing");
+                a.split_events = h->split_ev[h->ev_used++];
+            }
             e = launch_run_classifier(a);
             cudaError_t e2 = cudaFreeAsync(scratch, st);
             if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -260,8 +289,9 @@ void eikws_destroy(eikws_handle *h) {
     if (h->d_feat) cudaFree(h->d_feat);
     if (h->d_qfeat) cudaFree(h->d_qfeat);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    for (cudaEvent_t ev : h->split_ev)
-        if (ev) cudaEventDestroy(ev);
+    for (auto &triple : h->split_ev)
+        for (cudaEvent_t ev : triple)
+            if (ev) cudaEventDestroy(ev);
     if (h->pool) {
         cudaDeviceSynchronize();  // stream-ordered frees of the scratch may still be pending on callers' streams
         cudaMemPoolDestroy(h->pool);
@@ -316,27 +346,37 @@ int eikws_set_split(eikws_handle *h, int on) {  // tuning knob: the two-kernel c
     return EIKWS_OK;
 }
 // measurement aid (bench.py's roofline of the dominant kernel): with timing on, every split launch records CUDA events around its two
-// kernels on the launch stream; eikws_split_kernel_ms waits for the last launch and returns {spectral kernel, cepstral kernel} in ms
+// kernels on the launch stream.  eikws_split_kernel_ms waits for the recorded launches and returns the AVERAGE milliseconds per launch
+// of {spectral kernel, cepstral / classifier kernel} since timing was switched on (or since the last call), and how many launches that was.
 int eikws_set_kernel_timing(eikws_handle *h, int on) {
     if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
     DeviceGuard guard(h->device);
+    std::lock_guard<std::mutex> lock(h->mu);
     if (on)
-        for (cudaEvent_t &ev : h->split_ev)
-            if (!ev) {
-                cudaError_t e = cudaEventCreate(&ev);
-                if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
-            }
+        for (auto &triple : h->split_ev)
+            for (cudaEvent_t &ev : triple)
+                if (!ev) {
+                    cudaError_t e = cudaEventCreate(&ev);
+                    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+                }
     h->kernel_timing = on;
+    h->ev_used = 0;
+    h->ev_ms[0] = h->ev_ms[1] = 0.0;
+    h->ev_launches = 0;
     return EIKWS_OK;
 }
-int eikws_split_kernel_ms(eikws_handle *h, float *ms2) {
+int eikws_split_kernel_ms(eikws_handle *h, float *ms2, uint64_t *launches) {
     if (!h || !ms2) return EIKWS_ERR_BAD_ARG;
-    if (!h->split_ev[2]) return fail(EIKWS_ERR_BAD_ARG, "kernel timing is off");
     DeviceGuard guard(h->device);
-    cudaError_t e = cudaEventSynchronize(h->split_ev[2]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms2[0], h->split_ev[0], h->split_ev[1]);
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms2[1], h->split_ev[1], h->split_ev[2]);
-    if (e != cudaSuccess) return cuda_fail(e, "split kernel timing (no split launch recorded yet?)");
+    std::lock_guard<std::mutex> lock(h->mu);
+    cudaError_t e = harvest_split_events(h);
+    if (e != cudaSuccess) return cuda_fail(e, "split kernel timing");
+    if (h->ev_launches == 0) return fail(EIKWS_ERR_BAD_ARG, "no split launch has been timed (kernel timing off, or the launches took another path)");
+    ms2[0] = static_cast<float>(h->ev_ms[0] / static_cast<double>(h->ev_launches));
+    ms2[1] = static_cast<float>(h->ev_ms[1] / static_cast<double>(h->ev_launches));
+    if (launches) *launches = h->ev_launches;
+    h->ev_ms[0] = h->ev_ms[1] = 0.0;
+    h->ev_launches = 0;
     return EIKWS_OK;
 }
 int eikws_set_skew_ns(eikws_handle *h, int ns) {  // tuning knob (not in the public header)

@@ -225,8 +225,8 @@ int eikws_set_cmvn_shortcut(eikws_handle *h, int on);/* certified CMVN shortcut 
 int eikws_set_work_claiming(eikws_handle *h, int on);/* work-claiming schedule of the shortcut kernel                    */
 int eikws_set_pipelined(eikws_handle *h, int on);     /* software-pipelined classify kernel (two clips in different stages per CTA) */
 int eikws_set_split(eikws_handle *h, int on);         /* two-kernel classify path for int16 clips (default on): spectral kernel, then cepstral / classifier kernel */
-int eikws_set_kernel_timing(eikws_handle *h, int on); /* measurement aid: record CUDA events around the two kernels of every split launch */
-int eikws_split_kernel_ms(eikws_handle *h, float *ms2); /* waits for the last split launch: ms2[0] spectral kernel, ms2[1] cepstral / classifier kernel */
+int eikws_set_kernel_timing(eikws_handle *h, int on); /* measurement aid: record CUDA events around the two kernels of every split launch (device entry points; not for concurrent callers) */
+int eikws_split_kernel_ms(eikws_handle *h, float *ms2, uint64_t *launches); /* waits for the timed launches: average ms per launch of ms2[0] spectral kernel, ms2[1] cepstral / classifier kernel; resets the sums */
 int eikws_set_skew_ns(eikws_handle *h, int ns);      /* start offset between the CTAs that share an SM                   */
 
 /* ---- parity taps (tests only) --------------------------------------------------------------- */

@@ -19,7 +19,11 @@ d32 = (d16.to(torch.float32) / 32768.0).contiguous()
 quick = "--quick" in sys.argv  # racecheck: the default model only, every schedule / lowering knob
 # every lowering of the fused int8 path on the default model: mode 6 (default), 5, 4, 7 (two clip groups), 7 (one), 2
 imp = m.Impulse("l476")
-want = imp.run_classifier_device(d16).clone()
+want = imp.run_classifier_device(d16).clone()  # the two-kernel path (default for int16 clips)
+for m_clips in (1, 7, 8, 9, 163):  # work units that straddle clips / reach beyond the batch, CTAs with one clip
+    assert torch.equal(imp.run_classifier_device(d16[:m_clips].contiguous()), want[:m_clips]), m_clips
+imp.set_split(False)  # the fused kernel in every lowering
+assert torch.equal(imp.run_classifier_device(d16), want)
 for knobs in ({"work_claiming": False}, {"cmvn_shortcut": False}, {"tensor_core": False}, {"tensor_core": False, "clips_per_cta": 1},
               {"tensor_core": False, "cmvn_shortcut": False}):
     imp.set_work_claiming(knobs.get("work_claiming", True))

@@ -34,12 +34,9 @@ for rep in range(3):
 k = ""
 if split:
     imp.set_kernel_timing(True)
-    ka = kb = 0.0
     for _ in range(5):
         imp.run_classifier_device(clips, out=out)
-        x, y = imp.split_kernel_ms()
-        ka += x / 5
-        kb += y / 5
+    ka, kb, _ = imp.split_kernel_ms()
     k = "spectral %%.3f ms  cepstral %%.3f ms" %% (ka, kb)
 print("%%-22s split=%%d  %%.3f ms/step  %%7.3f M clips/s  equal=%%s  %%s" %% (os.path.basename(os.environ.get("EIKWS_B200_LIB", "in-tree")), split, best, n / best / 1e3, same, k), flush=True)
 """ % ROOT
