@@ -155,15 +155,16 @@ int launch(eikws_handle *h, const void *clips, bool f32, const float *features_i
     a.nn_smem_bytes = h->dev.nn_smem_bytes;
     a.stream = st;
     cudaError_t e;
-    if (h->split && !h->pipelined && clips && !f32 && !features_in && run_nn && a.nn_fused && !a.nn_float && a.nn_tc && a.cmvn_certified && !feat && !dbg &&
-        h->clips_per_cta == 2) {
+    if (h->split && !h->pipelined && clips && !features_in && run_nn && !feat && !dbg &&
+        (a.nn_float || (a.nn_fused && h->tensor_core != 0 && h->host.dev.nn.fused.tc_enabled != 0 && a.cmvn_certified && h->clips_per_cta == 2))) {
+        a.nn_tc = !a.nn_float;
         // two kernels per chunk, the log-mel records in between in stream-ordered scratch
         const size_t L = h->graph.labels.size();
         for (size_t off = 0; off < n; off += h->split_chunk_clips) {
             const size_t m = n - off < h->split_chunk_clips ? n - off : h->split_chunk_clips;
             void *scratch = nullptr;
             if ((e = cudaMallocFromPoolAsync(&scratch, split_scratch_bytes(m), h->pool, st)) != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(log-mel scratch)");
-            a.clips = static_cast<const int16_t *>(clips) + off * static_cast<size_t>(kSamples);
+            a.clips = static_cast<const char *>(clips) + off * static_cast<size_t>(kSamples) * (f32 ? 4 : 2);
             a.n_clips = m;
             a.probs = probs + off * L;
             a.qfeatures_out = qfeat ? qfeat + off * static_cast<size_t>(kFeatures) : nullptr;

@@ -626,3 +626,40 @@ def test_split_kernels_are_bit_identical(name, impulses, synth):
             assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p_ref[n - m:]), f"tail n={m}"
     finally:
         imp.set_split(True)
+
+
+@pytest.mark.parametrize("name,f32_input", [("l476", True), ("l476f32", False), ("l476f32", True), ("gsc12", True)])
+def test_split_kernels_float_clips_and_float_graph(name, f32_input, impulses, synth):
+    """the two-kernel path with float32 clips (spectral kernel on four-frame units, 65 chunks per frame) and / or the float32 graph
+    (eikws_cepstral_f32_kernel: the reference's CMVN chains + the float op plan): goldens of the unmodified reference, then the
+    fused kernel on fresh clips -- the two paths run the same device functions in the same order, so even the float probabilities
+    must be bit-identical -- and ragged batch sizes"""
+    import torch
+    imp = impulses[name]
+    g = golden(name)
+    clips = golden_clips(synth, g)
+    gin = (clips.astype(np.float32) / np.float32(32768.0)) if f32_input else clips
+    n = 8192 + 37
+    d = imp.synth_clips_device(n, first_clip=717171, seed=0xF10A7)
+    if f32_input:
+        d = (d.to(torch.float32) / 32768.0).contiguous()
+    try:
+        imp.set_split(False)
+        p_ref = imp.run_classifier_device(d).clone()
+        imp.set_split(True)
+        before = imp.launch_count
+        got = imp.run_classifier(gin)
+        assert imp.launch_count == before + 2, "the split path launches two kernels per chunk"
+        if name == "l476f32":
+            assert np.abs(got - g["probs"]).max() <= 1e-5  # float softmax: GPU expf vs glibc (north_star's tolerance)
+        else:
+            assert np.array_equal(got, g["probs"])
+        p1 = imp.run_classifier_device(d)
+        torch.cuda.synchronize()
+        bad = (p1 != p_ref).any(dim=1).nonzero().flatten()
+        assert bad.numel() == 0, f"clips whose probabilities differ from the fused kernel's: {bad[:10].tolist()}"
+        for m in (1, 2, 3, 4, 5, 163, 739, 741, 1481):
+            assert torch.equal(imp.run_classifier_device(d[:m].contiguous()), p_ref[:m]), f"n={m}"
+            assert torch.equal(imp.run_classifier_device(d[n - m:].contiguous()), p_ref[n - m:]), f"tail n={m}"
+    finally:
+        imp.set_split(True)
