@@ -224,7 +224,7 @@ int eikws_set_tensor_core(eikws_handle *h, int on);  /* block 1 of the fused cla
 int eikws_set_cmvn_shortcut(eikws_handle *h, int on);/* certified CMVN shortcut (0: every chain with the exact sequence) */
 int eikws_set_work_claiming(eikws_handle *h, int on);/* work-claiming schedule of the shortcut kernel                    */
 int eikws_set_pipelined(eikws_handle *h, int on);     /* software-pipelined classify kernel (two clips in different stages per CTA) */
-int eikws_set_split(eikws_handle *h, int on);         /* two-kernel classify path for int16 clips (default on): spectral kernel, then cepstral / classifier kernel */
+int eikws_set_split(eikws_handle *h, int on);         /* two-kernel classify path (default on; int16 or float32 clips, tensor-core int8 lowering or float32 graph): spectral kernel, then cepstral / classifier kernel; 0 = the single fused kernel */
 int eikws_set_kernel_timing(eikws_handle *h, int on); /* measurement aid: record CUDA events around the two kernels of every split launch (device entry points; not for concurrent callers) */
 int eikws_split_kernel_ms(eikws_handle *h, float *ms2, uint64_t *launches); /* waits for the timed launches: average ms per launch of ms2[0] spectral kernel, ms2[1] cepstral / classifier kernel; resets the sums */
 int eikws_set_skew_ns(eikws_handle *h, int ns);      /* start offset between the CTAs that share an SM                   */
