@@ -135,11 +135,17 @@ def test_tuning_knobs_are_exported_and_validate_their_arguments(eikws):
     for name in ("eikws_set_cmvn_shortcut", "eikws_set_work_claiming", "eikws_set_tensor_core", "eikws_set_clips_per_cta",
                  "eikws_set_ctas_per_sm", "eikws_set_skew_ns", "eikws_classify_taps_i16_device"):
         assert hasattr(lib, name), name
-    for name in ("eikws_set_cmvn_shortcut", "eikws_set_work_claiming", "eikws_set_tensor_core", "eikws_set_clips_per_cta"):
+    for name in ("eikws_set_cmvn_shortcut", "eikws_set_work_claiming", "eikws_set_tensor_core", "eikws_set_clips_per_cta", "eikws_set_split",
+                 "eikws_set_pipelined", "eikws_set_kernel_timing"):
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p, C.c_int]
         fn.restype = C.c_int
         assert fn(None, 1) != 0
+    # the kernel-timing query of the two-kernel path: null handle / null output refused
+    lib.eikws_split_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.eikws_split_kernel_ms.restype = C.c_int
+    ms = (C.c_float * 2)()
+    assert lib.eikws_split_kernel_ms(None, ms, None) != 0
 
 
 def _mutations(blob: bytes):
