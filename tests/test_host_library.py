@@ -280,3 +280,22 @@ def test_mix_audio_restatement_known_answers():
     assert np.array_equal(mo.mix_audio(None, bg, 100, 3.0, 2.0), np.full(16000, 0.5))  # background-only clip
     pcm = mo.to_pcm16(np.array([0.0, 1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767, 2.0, -1.0001]))
     assert pcm.tolist() == [0, 32767, -32767, 0, 2, 2, -2, 32766]  # ties to even; 65534 and -32770 wrap through 16 bits
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the unmodified reference on the host cores, no GPU, nothing of the product loaded): ONE JSON line with
+    the base contract's keys, impl = reference, a cpu_baseline describing the run and an e2e object repeating the value"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-clips-per-core", "128"],
+                         check=True, capture_output=True, text=True, timeout=600).stdout.strip().splitlines()
+    assert len(out) == 1, out
+    d = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "clips_per_sec" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["gpu_launches"] == 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
