@@ -272,8 +272,11 @@ int eikws_create(const void *model_blob, size_t bytes, int device, eikws_handle 
         props.location.id = device;
         uint64_t keep = UINT64_MAX;  // freed scratch stays in the pool: the next launch's allocation costs microseconds
         if ((e = cudaMemPoolCreate(&h->pool, &props)) != cudaSuccess || (e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) {
-            eikws_destroy(h);
-            return cuda_fail(e, "cudaMemPoolCreate");
+            // no stream-ordered allocator on this device / driver configuration: the handle still works, on the single fused kernel (which needs no scratch)
+            (void)cudaGetLastError();
+            if (h->pool) cudaMemPoolDestroy(h->pool);
+            h->pool = nullptr;
+            h->split = 0;
         }
     }
     *out = h;
@@ -343,6 +346,7 @@ int eikws_set_pipelined(eikws_handle *h, int on) {  // tuning knob: the software
 }
 int eikws_set_split(eikws_handle *h, int on) {  // tuning knob: the two-kernel classify path (spectral kernel + cepstral / classifier kernel)
     if (!h || (on != 0 && on != 1)) return EIKWS_ERR_BAD_ARG;
+    if (on && !h->pool) return fail(EIKWS_ERR_UNSUPPORTED, "the two-kernel path needs the stream-ordered allocator (cudaMemPoolCreate failed at eikws_create)");
     h->split = on;
     return EIKWS_OK;
 }
